@@ -1,0 +1,317 @@
+"""cpu-path-tracing_b200 -- Python binding (ctypes) of the C ABI in include/ptb200.h.
+
+This is plumbing for tests/ and bench.py: the product is libptb200.so (hand-written
+sm_100a CUDA behind a C ABI) driven from C++ (host/pt.hpp, host/ptb_main.cpp).  There
+is no CPU or PyTorch fallback anywhere in this package: if libptb200.so is missing,
+importing fails; if no CUDA device is usable, Renderer() raises.
+
+Load it with ``__graft_entry__.load_package()`` (the directory name has a hyphen).
+
+Mirrors the host flow of the reference's main (/root/reference/src/main.cpp:199-248):
+
+    scene  = pt::box_scene(w, h)                    -> builtin_scene("box_mirror", w, h)
+    cam    = pt::camera::with_config(scene.camera)  -> camera_with_config(cfg)
+    image  = vector<vec3>(w*h)                      -> Renderer.set_image(w, h, 2)
+    executor.run(taskflow).wait()                   -> Renderer.render(seed, first, samps)
+    (render_subpixel clamp/accumulate)              -> Renderer.resolve()
+    PPM output                                      -> write_ppm(path, rgb)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libptb200.so")
+
+SPHERE_BYTES = 88
+CAMERA_BYTES = 176
+CAMERA_CONFIG_BYTES = 112
+
+VARIANT_MEGAKERNEL = 0x0
+VARIANT_WAVEFRONT = 0x1
+PRECISION_FP32 = 0x00
+PRECISION_FP64 = 0x10
+
+DIFFUSE, SPECULAR, DIELECTRIC = 0, 1, 2
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C {HERE}` (or __graft_entry__.build()). "
+        "There is no CPU fallback.")
+
+_lib = ctypes.CDLL(LIB_PATH)
+
+_vp = ctypes.c_void_p
+_u32 = ctypes.c_uint32
+_u64 = ctypes.c_uint64
+_sz = ctypes.c_size_t
+
+
+class PtbError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"ptb status {code}: {message}")
+        self.code = code
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [
+        ("paths", _u64), ("rays", _u64), ("last_render_ms", ctypes.c_double), ("total_render_ms", ctypes.c_double),
+        ("kernel_launches", _u64), ("hits_diffuse", _u64), ("hits_specular", _u64), ("hits_dielectric", _u64),
+    ]
+
+
+@dataclass
+class Stats:
+    paths: int
+    rays: int
+    last_render_ms: float
+    total_render_ms: float
+    kernel_launches: int
+    hits_diffuse: int
+    hits_specular: int
+    hits_dielectric: int
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(_lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_ptb_abi_version = _sig("ptb_abi_version", ctypes.c_int)
+_ptb_device_count = _sig("ptb_device_count", ctypes.c_int)
+_ptb_last_error = _sig("ptb_last_error", ctypes.c_char_p, _vp)
+_ptb_create = _sig("ptb_create", ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp))
+_ptb_destroy = _sig("ptb_destroy", None, _vp)
+_ptb_set_stream = _sig("ptb_set_stream", ctypes.c_int, _vp, _vp)
+_ptb_synchronize = _sig("ptb_synchronize", ctypes.c_int, _vp)
+_ptb_upload_scene = _sig("ptb_upload_scene", ctypes.c_int, _vp, _vp, _sz, _sz)
+_ptb_set_camera = _sig("ptb_set_camera", ctypes.c_int, _vp, _vp, _sz)
+_ptb_set_image = _sig("ptb_set_image", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+_ptb_clear = _sig("ptb_clear", ctypes.c_int, _vp)
+_ptb_render = _sig("ptb_render", ctypes.c_int, _vp, _u64, _u32, _u32, _u32)
+_ptb_resolve = _sig("ptb_resolve", ctypes.c_int, _vp, _vp)
+_ptb_resolve_rgb8 = _sig("ptb_resolve_rgb8", ctypes.c_int, _vp, _vp)
+_ptb_accum_buffer = _sig("ptb_accum_buffer", ctypes.c_int, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz))
+_ptb_set_accum_buffer = _sig("ptb_set_accum_buffer", ctypes.c_int, _vp, _vp, _sz)
+_ptb_download_accum = _sig("ptb_download_accum", ctypes.c_int, _vp, _vp, _sz)
+_ptb_get_stats = _sig("ptb_get_stats", ctypes.c_int, _vp, ctypes.POINTER(_Stats))
+_ptb_trace_samples = _sig("ptb_trace_samples", ctypes.c_int, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp,
+                          _vp, _vp)
+_ptb_rng_draws = _sig("ptb_rng_draws", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, ctypes.c_int, _vp)
+_ptb_camera_with_config = _sig("ptb_camera_with_config", ctypes.c_int, _vp, _vp)
+_ptb_builtin_scene = _sig("ptb_builtin_scene", ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _vp, _sz,
+                          ctypes.POINTER(_sz), _vp)
+_ptb_write_ppm = _sig("ptb_write_ppm", ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.c_int)
+
+# every symbol include/ptb200.h declares (tests check the header against this list and the .so)
+EXPORTED_SYMBOLS = (
+    "ptb_abi_version", "ptb_device_count", "ptb_last_error", "ptb_create", "ptb_destroy", "ptb_set_stream",
+    "ptb_synchronize", "ptb_upload_scene", "ptb_set_camera", "ptb_set_image", "ptb_clear", "ptb_render",
+    "ptb_resolve", "ptb_resolve_rgb8", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
+    "ptb_get_stats", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
+    "ptb_write_ppm",
+)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def abi_version() -> int:
+    return _ptb_abi_version()
+
+
+def device_count() -> int:
+    return _ptb_device_count()
+
+
+# ---- host-side scene layer (no GPU needed) ---------------------------------------------------
+SPHERE_DTYPE = np.dtype([
+    ("radius", "<f8"), ("position", "<f8", 3), ("emission", "<f8", 3), ("color", "<f8", 3), ("reflection", "<i4"),
+    ("pad", "<i4"),
+])
+assert SPHERE_DTYPE.itemsize == SPHERE_BYTES
+CAMERA_CONFIG_DTYPE = np.dtype([
+    ("position", "<f8", 3), ("direction", "<f8", 3), ("up", "<f8", 3), ("aspect_ratio", "<f8"),
+    ("vertical_fov_radians", "<f8"), ("focal_length", "<f8"), ("aperture", "<f8"), ("focus_distance", "<f8"),
+])
+assert CAMERA_CONFIG_DTYPE.itemsize == CAMERA_CONFIG_BYTES
+CAMERA_DTYPE = np.dtype([
+    ("position", "<f8", 3), ("lower_left_corner", "<f8", 3), ("cam_x_axis", "<f8", 3), ("cam_y_axis", "<f8", 3),
+    ("u", "<f8", 3), ("v", "<f8", 3), ("w", "<f8", 3), ("lens_radius", "<f8"),
+])
+assert CAMERA_DTYPE.itemsize == CAMERA_BYTES
+
+BUILTIN_SCENES = ("simple", "box", "box_mirror", "dof_glass", "spheres10k")
+
+
+def builtin_scene(name: str, width: int, height: int):
+    """(spheres: SPHERE_DTYPE[n], camera_config: CAMERA_CONFIG_DTYPE[1]) of a built-in scene."""
+    n = _sz(0)
+    rc = _ptb_builtin_scene(name.encode(), width, height, None, 0, ctypes.byref(n), None)
+    if rc != 0:
+        raise PtbError(rc, f"unknown built-in scene {name!r} or bad size")
+    spheres = np.zeros(n.value, dtype=SPHERE_DTYPE)
+    cfg = np.zeros(1, dtype=CAMERA_CONFIG_DTYPE)
+    rc = _ptb_builtin_scene(name.encode(), width, height, _ptr(spheres), n.value, ctypes.byref(n), _ptr(cfg))
+    if rc != 0:
+        raise PtbError(rc, "ptb_builtin_scene")
+    return spheres, cfg
+
+
+def camera_with_config(cfg: np.ndarray) -> np.ndarray:
+    cfg = np.ascontiguousarray(cfg)
+    assert cfg.nbytes == CAMERA_CONFIG_BYTES
+    cam = np.zeros(1, dtype=CAMERA_DTYPE)
+    rc = _ptb_camera_with_config(_ptr(cfg), _ptr(cam))
+    if rc != 0:
+        raise PtbError(rc, "ptb_camera_with_config")
+    return cam
+
+
+def write_ppm(path: str, rgb: np.ndarray) -> None:
+    rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+    h, w, c = rgb.shape
+    assert c == 3
+    rc = _ptb_write_ppm(os.fsencode(path), _ptr(rgb), w, h)
+    if rc != 0:
+        raise PtbError(rc, f"ptb_write_ppm({path})")
+
+
+# ---- the GPU renderer ------------------------------------------------------------------------------
+class Renderer:
+    """One context = one GPU.  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self._ctx = _vp(None)
+        rc = _ptb_create(device, ctypes.byref(self._ctx))
+        if rc != 0:
+            msg = _ptb_last_error(None).decode()
+            self._ctx = _vp(None)
+            raise PtbError(rc, msg)
+        self.device = device
+        self.width = self.height = self.nsub = 0
+
+    # -- lifetime
+    def close(self):
+        if self._ctx:
+            _ptb_destroy(self._ctx)
+            self._ctx = _vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PtbError(rc, _ptb_last_error(self._ctx).decode())
+
+    # -- inputs
+    def upload_scene(self, spheres: np.ndarray, stride: int | None = None):
+        spheres = np.ascontiguousarray(spheres)
+        if spheres.dtype == np.uint8:
+            stride = stride or SPHERE_BYTES
+            count = spheres.size // stride
+        else:
+            stride = stride or spheres.dtype.itemsize
+            count = spheres.shape[0]
+        self._check(_ptb_upload_scene(self._ctx, _ptr(spheres), count, stride))
+
+    def set_camera(self, camera: np.ndarray):
+        camera = np.ascontiguousarray(camera)
+        self._check(_ptb_set_camera(self._ctx, _ptr(camera), camera.nbytes))
+
+    def set_image(self, width: int, height: int, num_subpixels: int = 2):
+        self._check(_ptb_set_image(self._ctx, width, height, num_subpixels))
+        self.width, self.height, self.nsub = width, height, num_subpixels
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(_ptb_set_stream(self._ctx, _vp(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self._check(_ptb_synchronize(self._ctx))
+
+    def clear(self):
+        self._check(_ptb_clear(self._ctx))
+
+    # -- hot path
+    def render(self, seed: int, first_sample: int, samples_per_subpixel: int, flags: int = 0):
+        self._check(_ptb_render(self._ctx, seed, first_sample, samples_per_subpixel, flags))
+
+    def resolve(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 3), dtype=np.float64)
+        self._check(_ptb_resolve(self._ctx, _ptr(out)))
+        return out
+
+    def resolve_into(self, out: np.ndarray):
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.height * self.width * 3
+        self._check(_ptb_resolve(self._ctx, _ptr(out)))
+
+    def resolve_rgb8(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        self._check(_ptb_resolve_rgb8(self._ctx, _ptr(out)))
+        return out
+
+    # -- multi-GPU plumbing
+    def accum_buffer(self):
+        p, n = _vp(None), _sz(0)
+        self._check(_ptb_accum_buffer(self._ctx, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def set_accum_buffer(self, device_ptr: int | None, nbytes: int = 0):
+        self._check(_ptb_set_accum_buffer(self._ctx, _vp(device_ptr) if device_ptr else None, nbytes))
+
+    def download_accum(self) -> np.ndarray:
+        out = np.empty((self.height * self.width * self.nsub * self.nsub, 4), dtype=np.float32)
+        self._check(_ptb_download_accum(self._ctx, _ptr(out), out.size))
+        return out
+
+    # -- introspection
+    def stats(self) -> Stats:
+        s = _Stats()
+        self._check(_ptb_get_stats(self._ctx, ctypes.byref(s)))
+        return Stats(*[getattr(s, f[0]) for f in _Stats._fields_])
+
+    def trace_samples(self, seed, xs, ys, sxs, sys_, samples, flags=PRECISION_FP64):
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, sxs, sys_, samples)]
+        count = arrs[0].size
+        hit = np.zeros(count, dtype=np.int32)
+        rad = np.zeros((count, 3), dtype=np.float64)
+        ray = np.zeros((count, 6), dtype=np.float64)
+        draws = np.zeros(count, dtype=np.uint32)
+        self._check(_ptb_trace_samples(self._ctx, seed, *[_ptr(a) for a in arrs], count, flags, _ptr(hit), _ptr(rad),
+                                       _ptr(ray), _ptr(draws)))
+        return hit, rad, ray, draws
+
+    def rng_draws(self, seed, slots, samples, n_draws) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        samples = np.ascontiguousarray(samples, dtype=np.uint32)
+        out = np.zeros((slots.size, n_draws), dtype=np.float64)
+        self._check(_ptb_rng_draws(self._ctx, seed, _ptr(slots), _ptr(samples), slots.size, n_draws, _ptr(out)))
+        return out
+
+
+def render_scene(name: str, width: int, height: int, spp: int, seed: int = 1, device: int = 0, flags: int = 0):
+    """The whole of the reference's main() for a built-in scene: returns the W*H*3 FP64 image."""
+    spheres, cfg = builtin_scene(name, width, height)
+    cam = camera_with_config(cfg)
+    with Renderer(device) as r:
+        r.upload_scene(spheres)
+        r.set_camera(cam)
+        r.set_image(width, height, 2)
+        r.render(seed, 0, spp // 4, flags)  # main.cpp:206: samps = spp / (2*2)
+        return r.resolve()

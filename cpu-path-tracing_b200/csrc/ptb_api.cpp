@@ -1,0 +1,898 @@
+// ptb_api.cpp -- the GPU-backed entry points of include/ptb200.h: context, scene
+// packing, render / resolve orchestration.  Host C++ only; kernels live in
+// ptb_f32.cu (throughput), ptb_f64.cu (parity), ptb_resolve.cu.
+//
+// There is deliberately no CPU path in this file: every compute entry point needs a
+// live context, and ptb_create fails when no CUDA device is usable.
+#include "../../include/ptb200.h"
+#include "ptb_kernels.h"
+#include "ptb_rng.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ptb;
+
+struct ptb_context
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr; // the one in use (own or caller's)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // scene
+    int n = 0;
+    bool have_scene = false, have_camera = false;
+    std::vector<RawSphere> h_spheres;
+    RawCamera h_camera{};
+    RawSphere* d_spheres = nullptr;
+    size_t d_spheres_cap = 0;
+    RawCamera* d_camera = nullptr;
+    ConstSceneF32 cs{};
+    double shift[3] = { 0, 0, 0 };
+    int n_small = 0, n_big = 0;
+    SmallGeo* d_small = nullptr;
+    BigGeo* d_big = nullptr;
+    int* d_small_id = nullptr;
+    int* d_big_id = nullptr;
+    float4* d_shade = nullptr; // 4 planes of n
+    size_t geo_cap = 0;
+
+    // image
+    int width = 0, height = 0, ns = 0;
+    size_t nslots = 0;
+    float4* d_accum = nullptr; // owned
+    size_t d_accum_bytes = 0;
+    float4* ext_accum = nullptr; // caller-owned
+    size_t ext_accum_bytes = 0;
+    double* d_accum64 = nullptr;
+    bool accum64_used = false;
+    double* d_rgb = nullptr;
+    uint8_t* d_rgb8 = nullptr;
+
+    DeviceCounters* d_counters = nullptr;
+    ptb_stats stats{};
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail_cuda(ptb_context* ctx, cudaError_t e, char const* what)
+{
+    ctx->err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return PTB_ERR_CUDA;
+}
+
+int fail(ptb_context* ctx, int code, char const* what)
+{
+    ctx->err = what;
+    return code;
+}
+
+#define PTB_CUDA(ctx, call) \
+    do { \
+        cudaError_t const e_ = (call); \
+        if(e_ != cudaSuccess) { \
+            return fail_cuda((ctx), e_, #call); \
+        } \
+    } while(0)
+
+float4* active_accum(ptb_context* ctx)
+{
+    return ctx->ext_accum != nullptr ? ctx->ext_accum : ctx->d_accum;
+}
+
+// Geometry class: spheres whose radius dwarfs the distances that matter need the
+// 2R-normalised form in binary32 (ptb_scene.cuh).  Absolute error of the classic
+// form near the surface is ~3e-8 * R in t; the reference's own absolute scale is
+// epsilon = 1e-4 (constants.hpp:7), so R > 32 moves to the stable form.
+constexpr double kBigRadius = 32.0;
+
+// Build the FP32 scene: origin shift, class split, FP64-precomputed coefficients.
+void pack_scene(ptb_context* ctx)
+{
+    int const n = ctx->n;
+    std::vector<RawSphere> const& s = ctx->h_spheres;
+
+    // origin shift = centroid of the ordinary-sized spheres (the region rays live in)
+    double cx = 0, cy = 0, cz = 0;
+    int m = 0;
+    for(int i = 0; i < n; ++i) {
+        if(s[i].radius <= kBigRadius) {
+            cx += s[i].px;
+            cy += s[i].py;
+            cz += s[i].pz;
+            ++m;
+        }
+    }
+    if(m > 0) {
+        cx /= m;
+        cy /= m;
+        cz /= m;
+    }
+    else if(ctx->have_camera) {
+        cx = ctx->h_camera.pos[0];
+        cy = ctx->h_camera.pos[1];
+        cz = ctx->h_camera.pos[2];
+    }
+    ctx->shift[0] = cx;
+    ctx->shift[1] = cy;
+    ctx->shift[2] = cz;
+}
+
+struct PackedScene
+{
+    std::vector<SmallGeo> small_geo;
+    std::vector<BigGeo> big_geo;
+    std::vector<int> small_id, big_id;
+    std::vector<float4> shade; // 4 planes
+};
+
+PackedScene pack_geometry(ptb_context* ctx)
+{
+    int const n = ctx->n;
+    std::vector<RawSphere> const& s = ctx->h_spheres;
+    double const* sh = ctx->shift;
+    PackedScene out;
+    out.shade.resize(static_cast<size_t>(4) * static_cast<size_t>(std::max(n, 1)));
+    for(int i = 0; i < n; ++i) {
+        double const R = s[i].radius;
+        double const x = s[i].px - sh[0], y = s[i].py - sh[1], z = s[i].pz - sh[2];
+        if(R > kBigRadius) {
+            double const k = 1.0 / (2.0 * R);
+            BigGeo b{};
+            b.gx = static_cast<float>(-k * x);
+            b.gy = static_cast<float>(-k * y);
+            b.gz = static_cast<float>(-k * z);
+            b.k = static_cast<float>(k);
+            b.K = static_cast<float>(k * ((x * x + y * y + z * z) - R * R));
+            b.two_r = static_cast<float>(2.0 * R);
+            out.big_geo.push_back(b);
+            out.big_id.push_back(i);
+        }
+        else {
+            SmallGeo g{};
+            g.cx = static_cast<float>(x);
+            g.cy = static_cast<float>(y);
+            g.cz = static_cast<float>(z);
+            g.r2 = static_cast<float>(R * R);
+            out.small_geo.push_back(g);
+            out.small_id.push_back(i);
+        }
+        double const inv_r = R != 0.0 ? 1.0 / R : 0.0;
+        double const p = std::max({ s[i].cr, s[i].cg, s[i].cb });
+        double const inv_p = p > 0.0 ? 1.0 / p : 0.0;
+        float4 a, b, c, d;
+        a.x = static_cast<float>(-x * inv_r);
+        a.y = static_cast<float>(-y * inv_r);
+        a.z = static_cast<float>(-z * inv_r);
+        a.w = static_cast<float>(inv_r);
+        b.x = static_cast<float>(s[i].er);
+        b.y = static_cast<float>(s[i].eg);
+        b.z = static_cast<float>(s[i].eb);
+        int32_t const refl = s[i].reflection;
+        std::memcpy(&b.w, &refl, sizeof(float));
+        c.x = static_cast<float>(s[i].cr);
+        c.y = static_cast<float>(s[i].cg);
+        c.z = static_cast<float>(s[i].cb);
+        c.w = static_cast<float>(p);
+        d.x = static_cast<float>(s[i].cr * inv_p);
+        d.y = static_cast<float>(s[i].cg * inv_p);
+        d.z = static_cast<float>(s[i].cb * inv_p);
+        d.w = 0.0f;
+        size_t const N = static_cast<size_t>(n);
+        out.shade[i] = a;
+        out.shade[N + i] = b;
+        out.shade[2 * N + i] = c;
+        out.shade[3 * N + i] = d;
+    }
+    return out;
+}
+
+void pack_camera(ptb_context* ctx)
+{
+    RawCamera const& c = ctx->h_camera;
+    double const* sh = ctx->shift;
+    CameraF32& o = ctx->cs.cam;
+    o.px = static_cast<float>(c.pos[0] - sh[0]);
+    o.py = static_cast<float>(c.pos[1] - sh[1]);
+    o.pz = static_cast<float>(c.pos[2] - sh[2]);
+    o.rx = static_cast<float>(c.llc[0] - c.pos[0]);
+    o.ry = static_cast<float>(c.llc[1] - c.pos[1]);
+    o.rz = static_cast<float>(c.llc[2] - c.pos[2]);
+    o.ax = static_cast<float>(c.ax[0]);
+    o.ay = static_cast<float>(c.ax[1]);
+    o.az = static_cast<float>(c.ax[2]);
+    o.bx = static_cast<float>(c.ay[0]);
+    o.by = static_cast<float>(c.ay[1]);
+    o.bz = static_cast<float>(c.ay[2]);
+    o.lens_radius = static_cast<float>(c.lens_radius);
+    o.inv_w = ctx->width > 0 ? static_cast<float>(1.0 / ctx->width) : 0.0f;
+    o.inv_h = ctx->height > 0 ? static_cast<float>(1.0 / ctx->height) : 0.0f;
+    o.sub_len = ctx->ns > 0 ? static_cast<float>(1.0 / ctx->ns) : 0.0f;
+}
+
+// (Re)build everything derived from (spheres, camera, image geometry) and push the
+// global-memory parts to the device.
+int rebuild_device_scene(ptb_context* ctx)
+{
+    pack_scene(ctx);
+    PackedScene const ps = pack_geometry(ctx);
+    pack_camera(ctx);
+    int const n = ctx->n;
+    ctx->n_small = static_cast<int>(ps.small_geo.size());
+    ctx->n_big = static_cast<int>(ps.big_geo.size());
+    ctx->cs.n_small = ctx->n_small;
+    ctx->cs.n_big = ctx->n_big;
+    ctx->cs.n_total = n;
+    for(int i = 0; i < std::min(ctx->n_small, kMaxConstSpheres); ++i) {
+        ctx->cs.small_geo[i] = ps.small_geo[static_cast<size_t>(i)];
+        ctx->cs.small_id[i] = ps.small_id[static_cast<size_t>(i)];
+    }
+    for(int i = 0; i < std::min(ctx->n_big, kMaxConstSpheres); ++i) {
+        ctx->cs.big_geo[i] = ps.big_geo[static_cast<size_t>(i)];
+        ctx->cs.big_id[i] = ps.big_id[static_cast<size_t>(i)];
+    }
+
+    size_t const cap = static_cast<size_t>(std::max(n, 1));
+    if(cap > ctx->geo_cap) {
+        cudaFree(ctx->d_small);
+        cudaFree(ctx->d_big);
+        cudaFree(ctx->d_small_id);
+        cudaFree(ctx->d_big_id);
+        cudaFree(ctx->d_shade);
+        ctx->d_small = nullptr;
+        ctx->d_big = nullptr;
+        ctx->d_small_id = nullptr;
+        ctx->d_big_id = nullptr;
+        ctx->d_shade = nullptr;
+        ctx->geo_cap = 0;
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_small, cap * sizeof(SmallGeo)));
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_big, cap * sizeof(BigGeo)));
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_small_id, cap * sizeof(int)));
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_big_id, cap * sizeof(int)));
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_shade, 4 * cap * sizeof(float4)));
+        ctx->geo_cap = cap;
+    }
+    cudaStream_t const st = ctx->stream;
+    if(ctx->n_small > 0) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ps.small_geo.data(), ps.small_geo.size() * sizeof(SmallGeo),
+                                      cudaMemcpyHostToDevice, st));
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_small_id, ps.small_id.data(), ps.small_id.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, st));
+    }
+    if(ctx->n_big > 0) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_big, ps.big_geo.data(), ps.big_geo.size() * sizeof(BigGeo),
+                                      cudaMemcpyHostToDevice, st));
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_id, ps.big_id.data(), ps.big_id.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, st));
+    }
+    if(n > 0) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_shade, ps.shade.data(), 4 * static_cast<size_t>(n) * sizeof(float4),
+                                      cudaMemcpyHostToDevice, st));
+    }
+    PTB_CUDA(ctx, cudaStreamSynchronize(st)); // ps goes out of scope
+    return PTB_OK;
+}
+
+ShadePlanes shade_planes(ptb_context* ctx)
+{
+    size_t const N = static_cast<size_t>(ctx->n);
+    ShadePlanes sp;
+    sp.a = ctx->d_shade;
+    sp.b = ctx->d_shade + N;
+    sp.c = ctx->d_shade + 2 * N;
+    sp.d = ctx->d_shade + 3 * N;
+    return sp;
+}
+
+GeoLists geo_lists(ptb_context* ctx)
+{
+    GeoLists g;
+    g.small_geo = ctx->d_small;
+    g.big_geo = ctx->d_big;
+    g.small_id = ctx->d_small_id;
+    g.big_id = ctx->d_big_id;
+    return g;
+}
+
+int require_ready(ptb_context* ctx, bool need_image)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(!ctx->have_scene) {
+        return fail(ctx, PTB_ERR_STATE, "no scene: call ptb_upload_scene first");
+    }
+    if(!ctx->have_camera) {
+        return fail(ctx, PTB_ERR_STATE, "no camera: call ptb_set_camera first");
+    }
+    if(need_image && (ctx->width <= 0 || active_accum(ctx) == nullptr)) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    return PTB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int ptb_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+char const* ptb_last_error(ptb_context const* ctx)
+{
+    return ctx != nullptr ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int ptb_create(int device, ptb_context** out)
+{
+    if(out == nullptr) {
+        g_create_error = "ptb_create: out is null";
+        return PTB_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if(e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        g_create_error = "ptb_create: no usable CUDA device (this library has no CPU path)";
+        return PTB_ERR_NO_DEVICE;
+    }
+    if(device < 0 || device >= n) {
+        g_create_error = "ptb_create: device index out of range";
+        return PTB_ERR_NO_DEVICE;
+    }
+    auto* ctx = new ptb_context{};
+    ctx->device = device;
+    auto bail = [&](cudaError_t err, char const* what) {
+        g_create_error = std::string("ptb_create: ") + what + ": " + cudaGetErrorString(err);
+        ptb_destroy(ctx);
+        return PTB_ERR_CUDA;
+    };
+    if((e = cudaSetDevice(device)) != cudaSuccess) {
+        return bail(e, "cudaSetDevice");
+    }
+    if((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
+        return bail(e, "cudaDeviceGetAttribute");
+    }
+    if((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        return bail(e, "cudaStreamCreate");
+    }
+    ctx->stream = ctx->own_stream;
+    if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        return bail(e, "cudaEventCreate");
+    }
+    if((e = cudaMalloc(&ctx->d_counters, sizeof(DeviceCounters))) != cudaSuccess) {
+        return bail(e, "cudaMalloc(counters)");
+    }
+    if((e = cudaMemset(ctx->d_counters, 0, sizeof(DeviceCounters))) != cudaSuccess) {
+        return bail(e, "cudaMemset(counters)");
+    }
+    if((e = cudaMalloc(&ctx->d_camera, sizeof(RawCamera))) != cudaSuccess) {
+        return bail(e, "cudaMalloc(camera)");
+    }
+    *out = ctx;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_context* ctx)
+{
+    if(ctx == nullptr) {
+        return;
+    }
+    cudaSetDevice(ctx->device);
+    if(ctx->own_stream != nullptr) {
+        cudaStreamSynchronize(ctx->own_stream);
+    }
+    cudaFree(ctx->d_spheres);
+    cudaFree(ctx->d_camera);
+    cudaFree(ctx->d_small);
+    cudaFree(ctx->d_big);
+    cudaFree(ctx->d_small_id);
+    cudaFree(ctx->d_big_id);
+    cudaFree(ctx->d_shade);
+    cudaFree(ctx->d_accum);
+    cudaFree(ctx->d_accum64);
+    cudaFree(ctx->d_rgb);
+    cudaFree(ctx->d_rgb8);
+    cudaFree(ctx->d_counters);
+    if(ctx->ev0 != nullptr) {
+        cudaEventDestroy(ctx->ev0);
+    }
+    if(ctx->ev1 != nullptr) {
+        cudaEventDestroy(ctx->ev1);
+    }
+    if(ctx->own_stream != nullptr) {
+        cudaStreamDestroy(ctx->own_stream);
+    }
+    delete ctx;
+}
+
+int ptb_set_stream(ptb_context* ctx, void* cuda_stream)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return PTB_OK;
+}
+
+int ptb_synchronize(ptb_context* ctx)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t stride)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(spheres == nullptr || count == 0 || stride < PTB_SPHERE_BYTES || count > (1u << 24)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need count >= 1 spheres of stride >= 88 bytes");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->h_spheres.resize(count);
+    auto const* src = static_cast<unsigned char const*>(spheres);
+    for(size_t i = 0; i < count; ++i) {
+        std::memcpy(static_cast<void*>(&ctx->h_spheres[i]), src + i * stride, PTB_SPHERE_BYTES);
+        ctx->h_spheres[i].pad_ = 0;
+        int const r = ctx->h_spheres[i].reflection;
+        if(r < 0 || r > 2) {
+            ctx->h_spheres.clear();
+            ctx->have_scene = false;
+            return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: reflection must be 0 (diffuse), 1 (specular) or 2 (dielectric)");
+        }
+    }
+    ctx->n = static_cast<int>(count);
+    if(count > ctx->d_spheres_cap) {
+        cudaFree(ctx->d_spheres);
+        ctx->d_spheres = nullptr;
+        ctx->d_spheres_cap = 0;
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_spheres, count * sizeof(RawSphere)));
+        ctx->d_spheres_cap = count;
+    }
+    PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_spheres, ctx->h_spheres.data(), count * sizeof(RawSphere),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_scene = true;
+    return rebuild_device_scene(ctx);
+}
+
+int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(camera == nullptr || bytes != PTB_CAMERA_BYTES) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_camera: need a 176-byte pt::camera");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::memcpy(static_cast<void*>(&ctx->h_camera), camera, sizeof(RawCamera));
+    PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_camera, &ctx->h_camera, sizeof(RawCamera), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_camera = true;
+    if(ctx->have_scene) {
+        return rebuild_device_scene(ctx);
+    }
+    return PTB_OK;
+}
+
+int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(width <= 0 || height <= 0 || num_subpixels <= 0 || num_subpixels > 8 ||
+       static_cast<unsigned long long>(width) * static_cast<unsigned long long>(height) *
+               static_cast<unsigned long long>(num_subpixels * num_subpixels) >=
+           (1ull << 31)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_image: bad geometry (need 1 <= num_subpixels <= 8 and < 2^31 sub-pixels)");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->width = width;
+    ctx->height = height;
+    ctx->ns = num_subpixels;
+    ctx->nslots = static_cast<size_t>(width) * static_cast<size_t>(height) * static_cast<size_t>(num_subpixels * num_subpixels);
+    size_t const bytes = ctx->nslots * sizeof(float4);
+    if(bytes > ctx->d_accum_bytes) {
+        cudaFree(ctx->d_accum);
+        ctx->d_accum = nullptr;
+        ctx->d_accum_bytes = 0;
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_accum, bytes));
+        ctx->d_accum_bytes = bytes;
+    }
+    cudaFree(ctx->d_accum64);
+    ctx->d_accum64 = nullptr;
+    ctx->accum64_used = false;
+    cudaFree(ctx->d_rgb);
+    cudaFree(ctx->d_rgb8);
+    ctx->d_rgb = nullptr;
+    ctx->d_rgb8 = nullptr;
+    size_t const npix = static_cast<size_t>(width) * static_cast<size_t>(height);
+    PTB_CUDA(ctx, cudaMalloc(&ctx->d_rgb, npix * 3 * sizeof(double)));
+    PTB_CUDA(ctx, cudaMalloc(&ctx->d_rgb8, npix * 3));
+    if(ctx->ext_accum != nullptr && ctx->ext_accum_bytes < bytes) {
+        ctx->ext_accum = nullptr;
+        ctx->ext_accum_bytes = 0;
+    }
+    if(ctx->have_camera) {
+        pack_camera(ctx);
+    }
+    return ptb_clear(ctx);
+}
+
+int ptb_clear(ptb_context* ctx)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if(active_accum(ctx) != nullptr && ctx->nslots > 0) {
+        PTB_CUDA(ctx, cudaMemsetAsync(active_accum(ctx), 0, ctx->nslots * sizeof(float4), ctx->stream));
+    }
+    if(ctx->d_accum64 != nullptr) {
+        PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum64, 0, ctx->nslots * 4 * sizeof(double), ctx->stream));
+    }
+    ctx->accum64_used = false;
+    PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t const launches = ctx->stats.kernel_launches;
+    ctx->stats = ptb_stats{};
+    ctx->stats.kernel_launches = launches;
+    return PTB_OK;
+}
+
+int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t samples_per_subpixel, uint32_t flags)
+{
+    int rc = require_ready(ctx, true);
+    if(rc != PTB_OK) {
+        return rc;
+    }
+    uint32_t const variant = flags & PTB_VARIANT_MASK;
+    uint32_t const precision = flags & PTB_PRECISION_MASK;
+    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK)) != 0 || variant > PTB_VARIANT_WAVEFRONT ||
+       (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
+    }
+    if(variant == PTB_VARIANT_WAVEFRONT) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: the wavefront variant is not built yet");
+    }
+    if(static_cast<uint64_t>(first_sample) + samples_per_subpixel > 0xFFFFFFFFull) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: sample range overflows 32 bits");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if(samples_per_subpixel == 0) {
+        ctx->stats.last_render_ms = 0.0;
+        return PTB_OK; // the reference renders a black image for spp < 4 (main.cpp:206)
+    }
+    cudaStream_t const st = ctx->stream;
+    uint64_t const key = seed_key(seed);
+    int launches = 0;
+
+    PTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    if(precision == PTB_PRECISION_FP64) {
+        if(ctx->d_accum64 == nullptr) {
+            PTB_CUDA(ctx, cudaMalloc(&ctx->d_accum64, ctx->nslots * 4 * sizeof(double)));
+            PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum64, 0, ctx->nslots * 4 * sizeof(double), st));
+        }
+        ctx->accum64_used = true;
+        PTB_CUDA(ctx, launch_render_f64(key, first_sample, samples_per_subpixel, static_cast<uint32_t>(ctx->width),
+                                        static_cast<uint32_t>(ctx->height), static_cast<uint32_t>(ctx->ns),
+                                        ctx->d_spheres, ctx->n, ctx->d_camera, ctx->d_accum64, ctx->d_counters, st));
+        launches = 1;
+    }
+    else {
+        PTB_CUDA(ctx, upload_const_scene(ctx->cs, st));
+        RenderParamsF32 p{};
+        p.key = key;
+        p.first_sample = first_sample;
+        p.samples = samples_per_subpixel;
+        p.width = static_cast<uint32_t>(ctx->width);
+        p.height = static_cast<uint32_t>(ctx->height);
+        p.ns = static_cast<uint32_t>(ctx->ns);
+        p.nslots = static_cast<uint32_t>(ctx->nslots);
+        p.ngroups = (p.nslots + 31u) / 32u;
+        // tile = 32 slots x chunk samples; aim for >= 16 tiles per resident warp so the
+        // tail of the launch is short, but keep tiles >= 8 samples deep
+        uint64_t const resident_warps = static_cast<uint64_t>(ctx->sm_count) * 64ull;
+        uint32_t chunk = samples_per_subpixel;
+        while(chunk > 8u && static_cast<uint64_t>(p.ngroups) * ((samples_per_subpixel + chunk - 1u) / chunk) < 16ull * resident_warps) {
+            chunk = (chunk + 1u) / 2u;
+        }
+        p.chunk = chunk;
+        p.nchunks = (samples_per_subpixel + chunk - 1u) / chunk;
+        p.ntiles = p.ngroups * p.nchunks;
+        p.accum = active_accum(ctx);
+        p.counters = ctx->d_counters;
+        p.shade = shade_planes(ctx);
+        p.geo = geo_lists(ctx);
+        p.n_total = ctx->n;
+        int const ns_spec = ctx->n_small <= kMaxConstSpheres && ctx->n_big <= kMaxConstSpheres ? ctx->n_small : -1;
+        PTB_CUDA(ctx, launch_megakernel(p, ns_spec, ctx->n_big, ctx->sm_count, st, &launches));
+    }
+    PTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    PTB_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.0f;
+    PTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.last_render_ms = ms;
+    ctx->stats.total_render_ms += ms;
+    ctx->stats.kernel_launches += static_cast<uint64_t>(launches);
+    ctx->stats.paths += static_cast<uint64_t>(ctx->nslots) * samples_per_subpixel;
+    return PTB_OK;
+}
+
+static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
+{
+    int rc = require_ready(ctx, true);
+    if(rc != PTB_OK) {
+        return rc;
+    }
+    if(rgb_out == nullptr && rgb8_out == nullptr) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_resolve: output pointer is null");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t const st = ctx->stream;
+    size_t const npix = static_cast<size_t>(ctx->width) * static_cast<size_t>(ctx->height);
+    PTB_CUDA(ctx, launch_resolve(active_accum(ctx), ctx->accum64_used ? ctx->d_accum64 : nullptr,
+                                 static_cast<uint32_t>(ctx->width), static_cast<uint32_t>(ctx->height),
+                                 static_cast<uint32_t>(ctx->ns), rgb_out != nullptr ? ctx->d_rgb : nullptr,
+                                 rgb8_out != nullptr ? ctx->d_rgb8 : nullptr, st));
+    ctx->stats.kernel_launches += 1;
+    if(rgb_out != nullptr) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(rgb_out, ctx->d_rgb, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if(rgb8_out != nullptr) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(rgb8_out, ctx->d_rgb8, npix * 3, cudaMemcpyDeviceToHost, st));
+    }
+    PTB_CUDA(ctx, cudaStreamSynchronize(st));
+    return PTB_OK;
+}
+
+int ptb_resolve(ptb_context* ctx, double* rgb_out)
+{
+    return resolve_common(ctx, rgb_out, nullptr);
+}
+
+int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out)
+{
+    return resolve_common(ctx, nullptr, rgb8_out);
+}
+
+int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes)
+{
+    if(ctx == nullptr || device_ptr == nullptr || bytes == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(active_accum(ctx) == nullptr) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    *device_ptr = active_accum(ctx);
+    *bytes = ctx->nslots * sizeof(float4);
+    return PTB_OK;
+}
+
+int ptb_set_accum_buffer(ptb_context* ctx, void* device_ptr, size_t bytes)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(device_ptr == nullptr) {
+        ctx->ext_accum = nullptr;
+        ctx->ext_accum_bytes = 0;
+        return PTB_OK;
+    }
+    if(ctx->width <= 0) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(bytes < ctx->nslots * sizeof(float4) || (reinterpret_cast<uintptr_t>(device_ptr) & 15u) != 0) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_accum_buffer: need a 16-byte aligned buffer of width*height*ns*ns*16 bytes");
+    }
+    ctx->ext_accum = static_cast<float4*>(device_ptr);
+    ctx->ext_accum_bytes = bytes;
+    return PTB_OK;
+}
+
+int ptb_download_accum(ptb_context* ctx, float* out, size_t floats)
+{
+    if(ctx == nullptr || out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(active_accum(ctx) == nullptr) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(floats < ctx->nslots * 4) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_download_accum: output too small");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaMemcpyAsync(out, active_accum(ctx), ctx->nslots * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_get_stats(ptb_context* ctx, ptb_stats* out)
+{
+    if(ctx == nullptr || out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DeviceCounters c{};
+    PTB_CUDA(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.rays = c.rays;
+    ctx->stats.hits_diffuse = c.diffuse;
+    ctx->stats.hits_specular = c.specular;
+    ctx->stats.hits_dielectric = c.dielectric;
+    *out = ctx->stats;
+    return PTB_OK;
+}
+
+int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,
+                      uint32_t const* sy, uint32_t const* sample, size_t count, uint32_t flags, int32_t* primary_hit_out,
+                      double* radiance_out, double* ray_out, uint32_t* draws_out)
+{
+    int rc = require_ready(ctx, false);
+    if(rc != PTB_OK) {
+        return rc;
+    }
+    if(ctx->width <= 0) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(x == nullptr || y == nullptr || sx == nullptr || sy == nullptr || sample == nullptr || primary_hit_out == nullptr ||
+       radiance_out == nullptr || count > (1u << 30)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: null pointer");
+    }
+    uint32_t const precision = flags & PTB_PRECISION_MASK;
+    if(precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: unknown flags");
+    }
+    for(size_t i = 0; i < count; ++i) {
+        if(x[i] >= static_cast<uint32_t>(ctx->width) || y[i] >= static_cast<uint32_t>(ctx->height) ||
+           sx[i] >= static_cast<uint32_t>(ctx->ns) || sy[i] >= static_cast<uint32_t>(ctx->ns)) {
+            return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: coordinate outside the image");
+        }
+    }
+    if(count == 0) {
+        return PTB_OK;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t const st = ctx->stream;
+    uint32_t* d_in = nullptr;
+    int32_t* d_hit = nullptr;
+    double* d_rad = nullptr;
+    double* d_ray = nullptr;
+    uint32_t* d_draws = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_in);
+        cudaFree(d_hit);
+        cudaFree(d_rad);
+        cudaFree(d_ray);
+        cudaFree(d_draws);
+    };
+#define PTB_CUDA_T(call) \
+    do { \
+        cudaError_t const e_ = (call); \
+        if(e_ != cudaSuccess) { \
+            cleanup(); \
+            return fail_cuda(ctx, e_, #call); \
+        } \
+    } while(0)
+    PTB_CUDA_T(cudaMalloc(&d_in, 5 * count * sizeof(uint32_t)));
+    PTB_CUDA_T(cudaMalloc(&d_hit, count * sizeof(int32_t)));
+    PTB_CUDA_T(cudaMalloc(&d_rad, 3 * count * sizeof(double)));
+    PTB_CUDA_T(cudaMalloc(&d_ray, 6 * count * sizeof(double)));
+    PTB_CUDA_T(cudaMalloc(&d_draws, count * sizeof(uint32_t)));
+    uint32_t const* srcs[5] = { x, y, sx, sy, sample };
+    for(int k = 0; k < 5; ++k) {
+        PTB_CUDA_T(cudaMemcpyAsync(d_in + static_cast<size_t>(k) * count, srcs[k], count * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, st));
+    }
+    ProbeParams q{};
+    q.key = seed_key(seed);
+    q.width = static_cast<uint32_t>(ctx->width);
+    q.height = static_cast<uint32_t>(ctx->height);
+    q.ns = static_cast<uint32_t>(ctx->ns);
+    q.x = d_in;
+    q.y = d_in + count;
+    q.sx = d_in + 2 * count;
+    q.sy = d_in + 3 * count;
+    q.sample = d_in + 4 * count;
+    q.count = static_cast<uint32_t>(count);
+    q.primary_hit = d_hit;
+    q.radiance = d_rad;
+    q.ray = d_ray;
+    q.draws = d_draws;
+    if(precision == PTB_PRECISION_FP64) {
+        PTB_CUDA_T(launch_probe_f64(q, ctx->d_spheres, ctx->n, ctx->d_camera, st));
+    }
+    else {
+        PTB_CUDA_T(upload_const_scene(ctx->cs, st));
+        PTB_CUDA_T(launch_probe_f32(q, shade_planes(ctx), geo_lists(ctx), st));
+    }
+    ctx->stats.kernel_launches += 1;
+    PTB_CUDA_T(cudaMemcpyAsync(primary_hit_out, d_hit, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PTB_CUDA_T(cudaMemcpyAsync(radiance_out, d_rad, 3 * count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if(ray_out != nullptr) {
+        PTB_CUDA_T(cudaMemcpyAsync(ray_out, d_ray, 6 * count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if(draws_out != nullptr) {
+        PTB_CUDA_T(cudaMemcpyAsync(draws_out, d_draws, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    PTB_CUDA_T(cudaStreamSynchronize(st));
+    if(ray_out != nullptr && precision == PTB_PRECISION_FP32) {
+        // FP32 rays live in the shifted frame: report them in world coordinates
+        for(size_t i = 0; i < count; ++i) {
+            ray_out[6 * i + 0] += ctx->shift[0];
+            ray_out[6 * i + 1] += ctx->shift[1];
+            ray_out[6 * i + 2] += ctx->shift[2];
+        }
+    }
+    cleanup();
+#undef PTB_CUDA_T
+    return PTB_OK;
+}
+
+int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_t const* sample, size_t count,
+                  int n_draws, double* draws_out)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(slot == nullptr || sample == nullptr || draws_out == nullptr || n_draws <= 0 || count == 0 || count > (1u << 28)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_rng_draws: bad arguments");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t const st = ctx->stream;
+    uint32_t* d_in = nullptr;
+    double* d_out = nullptr;
+    size_t const total = count * static_cast<size_t>(n_draws);
+    cudaError_t e = cudaMalloc(&d_in, 2 * count * sizeof(uint32_t));
+    if(e == cudaSuccess) {
+        e = cudaMalloc(&d_out, total * sizeof(double));
+    }
+    if(e == cudaSuccess) {
+        e = cudaMemcpyAsync(d_in, slot, count * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    }
+    if(e == cudaSuccess) {
+        e = cudaMemcpyAsync(d_in + count, sample, count * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    }
+    if(e == cudaSuccess) {
+        e = launch_rng_draws(seed_key(seed), d_in, d_in + count, static_cast<uint32_t>(count), n_draws, d_out, st);
+    }
+    if(e == cudaSuccess) {
+        e = cudaMemcpyAsync(draws_out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    if(e == cudaSuccess) {
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    ctx->stats.kernel_launches += 1;
+    if(e != cudaSuccess) {
+        return fail_cuda(ctx, e, "ptb_rng_draws");
+    }
+    return PTB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,297 @@
+// ptb_f32.cu -- FP32 throughput kernels: the persistent megakernel and the FP32 probe.
+//
+// Replaces the row-parallel CPU loop of /root/reference/src/main.cpp:217-236 (768
+// taskflow row tasks, each walking x, sy, sx, s sequentially with one mt19937).
+//
+// Megakernel design (B200: 148 SMs, 4 schedulers/SM, FP32 issue-bound, no tensor work):
+//   * persistent grid: SM count x resident blocks; warps pull WORK TILES
+//     (32 consecutive sub-pixel slots x `chunk` samples) from one global cursor, so
+//     the tail of the launch is one tile, not one wave;
+//   * inside a tile the 32 lanes share a pool of (slot, sample) items.  A lane whose
+//     path ended takes the next item of the pool at the top of the loop ("path
+//     regeneration"), so the closest-hit scan -- >80 % of the instructions -- always
+//     runs with every lane busy, whatever the spread of path lengths (geometric,
+//     mean 12.3 bounces, limit 100 in the box scenes);
+//   * the random stream is keyed by (seed, slot, sample), so which lane traces which
+//     item does not change the image;
+//   * sphere geometry is read as constant-bank operands of the FFMA/FADD
+//     instructions (kernels are specialised on the two list lengths and fully
+//     unrolled); shading planes sit in shared memory as float4 SoA;
+//   * a finished path adds {r,g,b,1} to its slot with ONE 16-byte vector reduction
+//     (red.global.add.v4.f32, sm_90+): no read-modify-write, no per-thread image
+//     state, progressive by construction.
+#include "ptb_kernels.h"
+#include "ptb_path_f32.cuh"
+
+namespace ptb {
+
+__constant__ ConstSceneF32 c_scene;
+
+constexpr int kMegaThreads = 128;
+
+cudaError_t upload_const_scene(ConstSceneF32 const& cs, cudaStream_t stream)
+{
+    return cudaMemcpyToSymbolAsync(c_scene, &cs, sizeof(cs), 0, cudaMemcpyHostToDevice, stream);
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z, float w)
+{
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :
+                 : "l"(addr), "f"(x), "f"(y), "f"(z), "f"(w)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+    return __reduce_add_sync(0xffffffffu, v);
+}
+
+template<int NS, int NB, bool kSmemShade>
+__global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 const prm)
+{
+    __shared__ float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
+    ShadePlanes sp = prm.shade;
+    if constexpr(kSmemShade) {
+        for(int i = threadIdx.x; i < prm.n_total; i += kMegaThreads) {
+            s_shade[i] = prm.shade.a[i];
+            s_shade[kSmemShadeSpheres + i] = prm.shade.b[i];
+            s_shade[2 * kSmemShadeSpheres + i] = prm.shade.c[i];
+            s_shade[3 * kSmemShadeSpheres + i] = prm.shade.d[i];
+        }
+        __syncthreads();
+        sp.a = s_shade;
+        sp.b = s_shade + kSmemShadeSpheres;
+        sp.c = s_shade + 2 * kSmemShadeSpheres;
+        sp.d = s_shade + 3 * kSmemShadeSpheres;
+    }
+
+    uint32_t const lane = threadIdx.x & 31u;
+    uint32_t const lt_mask = (1u << lane) - 1u;
+
+    // warp-uniform tile state
+    uint32_t tile_slot0 = 0, tile_sample0 = 0, tile_items = 0, next_item = 0;
+    bool exhausted = false;
+
+    bool alive = false;
+    uint32_t slot = 0;
+    PathF32 p;
+    BounceCounters cnt{ 0, 0, 0, 0 };
+
+    for(;;) {
+        uint32_t const need = __ballot_sync(0xffffffffu, !alive);
+        if(need != 0u && !exhausted) {
+            if(next_item >= tile_items) {
+                unsigned long long t = 0;
+                if(lane == 0) {
+                    t = atomicAdd(&prm.counters->tile_cursor, 1ull);
+                }
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if(t >= prm.ntiles) {
+                    exhausted = true;
+                }
+                else {
+                    uint32_t const tile = static_cast<uint32_t>(t);
+                    uint32_t const group = tile / prm.nchunks;
+                    uint32_t const chunk = tile - group * prm.nchunks;
+                    tile_slot0 = group * 32u;
+                    tile_sample0 = chunk * prm.chunk;
+                    tile_items = 32u * min(prm.chunk, prm.samples - tile_sample0);
+                    next_item = 0;
+                }
+            }
+            if(!exhausted) {
+                uint32_t const my = next_item + __popc(need & lt_mask);
+                if(!alive && my < tile_items) {
+                    slot = tile_slot0 + (my & 31u);
+                    if(slot < prm.nslots) {
+                        uint32_t const sample = prm.first_sample + tile_sample0 + (my >> 5);
+                        p.rng = rng_open(prm.key, slot, sample);
+                        uint32_t x, y, sx, sy;
+                        slot_coords(slot, prm.width, prm.ns, x, y, sx, sy);
+                        gen_primary(p, c_scene.cam, x, y, sx, sy);
+                        alive = true;
+                    }
+                }
+                next_item += __popc(need);
+            }
+        }
+        if(!__any_sync(0xffffffffu, alive)) {
+            if(exhausted) {
+                break;
+            }
+            continue;
+        }
+        if(alive) {
+            RayTerms const r = ray_terms(p);
+            float t;
+            int id;
+            bool const hit = closest_hit<NS, NB>(c_scene, prm.geo, p, r, t, id);
+            cnt.rays++;
+            alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
+            if(!alive) {
+                red_add_v4(prm.accum + slot, p.er, p.eg, p.eb, 1.0f);
+            }
+        }
+    }
+
+    uint32_t const rays = warp_sum(cnt.rays);
+    uint32_t const nd = warp_sum(cnt.diffuse);
+    uint32_t const nsp = warp_sum(cnt.specular);
+    uint32_t const ndi = warp_sum(cnt.dielectric);
+    if(lane == 0) {
+        atomicAdd(&prm.counters->rays, static_cast<unsigned long long>(rays));
+        atomicAdd(&prm.counters->diffuse, static_cast<unsigned long long>(nd));
+        atomicAdd(&prm.counters->specular, static_cast<unsigned long long>(nsp));
+        atomicAdd(&prm.counters->dielectric, static_cast<unsigned long long>(ndi));
+    }
+}
+
+// ---- specialisation table ------------------------------------------------------------------
+// (n_small, n_big) pairs with a fully unrolled kernel.  Everything else runs the
+// generic run-time-count variant.
+#define PTB_MEGA_SPECIALISATIONS(X) \
+    X(3, 5) /* box_scene.hpp / box_mirror_scene.hpp: 3 small spheres + 5 R=1e6 walls */ \
+    X(4, 1) /* simple_scene.hpp and the depth-of-field glass scene: 4 small + ground  */ \
+    X(5, 0) \
+    X(8, 0) \
+    X(1, 0) \
+    X(0, 1)
+
+bool megakernel_has_specialisation(int n_small, int n_big)
+{
+#define X(a, b) \
+    if(n_small == (a) && n_big == (b)) { \
+        return true; \
+    }
+    PTB_MEGA_SPECIALISATIONS(X)
+#undef X
+    return false;
+}
+
+template<int NS, int NB, bool kSmem>
+static cudaError_t launch_one(RenderParamsF32 const& p, int sm_count, cudaStream_t stream)
+{
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel<NS, NB, kSmem>, kMegaThreads, 0);
+    if(e != cudaSuccess) {
+        return e;
+    }
+    if(per_sm < 1) {
+        per_sm = 1;
+    }
+    unsigned long long const warps_needed = (static_cast<unsigned long long>(p.ntiles) + 0ull);
+    unsigned long long blocks = static_cast<unsigned long long>(sm_count) * static_cast<unsigned long long>(per_sm);
+    unsigned long long const blocks_needed = (warps_needed + (kMegaThreads / 32) - 1) / (kMegaThreads / 32);
+    if(blocks > blocks_needed) {
+        blocks = blocks_needed;
+    }
+    if(blocks < 1) {
+        blocks = 1;
+    }
+    mega_kernel<NS, NB, kSmem><<<static_cast<unsigned>(blocks), kMegaThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_megakernel(RenderParamsF32 const& p, int n_small, int n_big, int sm_count, cudaStream_t stream,
+                              int* launches)
+{
+    cudaError_t e = cudaMemsetAsync(&p.counters->tile_cursor, 0, sizeof(unsigned long long), stream);
+    if(e != cudaSuccess) {
+        return e;
+    }
+    if(launches != nullptr) {
+        *launches += 1;
+    }
+    bool const smem = p.n_total <= kSmemShadeSpheres;
+#define X(a, b) \
+    if(n_small == (a) && n_big == (b) && smem) { \
+        return launch_one<(a), (b), true>(p, sm_count, stream); \
+    }
+    PTB_MEGA_SPECIALISATIONS(X)
+#undef X
+    if(smem) {
+        return launch_one<-1, -1, true>(p, sm_count, stream);
+    }
+    return launch_one<-1, -1, false>(p, sm_count, stream);
+}
+
+// ---- FP32 probe ---------------------------------------------------------------------------------
+// One thread per requested sample; same device functions as the megakernel.
+__global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoLists const geo)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= q.count) {
+        return;
+    }
+    uint32_t const x = q.x[i], y = q.y[i], sx = q.sx[i], sy = q.sy[i];
+    uint32_t const slot = ((y * q.width + x) * q.ns + sy) * q.ns + sx;
+    PathF32 p;
+    p.rng = rng_open(q.key, slot, q.sample[i]);
+    gen_primary(p, c_scene.cam, x, y, sx, sy);
+    if(q.ray != nullptr) {
+        q.ray[6 * i + 0] = p.ox;
+        q.ray[6 * i + 1] = p.oy;
+        q.ray[6 * i + 2] = p.oz;
+        q.ray[6 * i + 3] = p.dx;
+        q.ray[6 * i + 4] = p.dy;
+        q.ray[6 * i + 5] = p.dz;
+    }
+    q.primary_hit[i] = primary_hit_index<-1, -1>(c_scene, geo, p);
+
+    BounceCounters cnt{ 0, 0, 0, 0 };
+    bool alive = true;
+    while(alive) {
+        RayTerms const r = ray_terms(p);
+        float t;
+        int id;
+        bool const hit = closest_hit<-1, -1>(c_scene, geo, p, r, t, id);
+        alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
+    }
+    q.radiance[3 * i + 0] = p.er;
+    q.radiance[3 * i + 1] = p.eg;
+    q.radiance[3 * i + 2] = p.eb;
+    if(q.draws != nullptr) {
+        q.draws[i] = 0;
+    }
+}
+
+cudaError_t launch_probe_f32(ProbeParams const& p, ShadePlanes const& shade, GeoLists const& geo, cudaStream_t stream)
+{
+    if(p.count == 0) {
+        return cudaSuccess;
+    }
+    unsigned const threads = 128;
+    unsigned const blocks = (p.count + threads - 1) / threads;
+    probe_f32_kernel<<<blocks, threads, 0, stream>>>(p, shade, geo);
+    return cudaGetLastError();
+}
+
+// ---- raw draws of the stream (device side), for tests/test_rng.py ----------------------------------
+__global__ void rng_draws_kernel(uint64_t key, uint32_t const* slot, uint32_t const* sample, uint32_t count, int n_draws,
+                                 double* out)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= count) {
+        return;
+    }
+    Rng g = rng_open(key, slot[i], sample[i]);
+    for(int k = 0; k < n_draws; ++k) {
+        // odd draws go through the FP32 path, even through the FP64 path: both must
+        // give the same 23-bit value
+        out[static_cast<size_t>(i) * n_draws + k] = (k & 1) ? static_cast<double>(rng_uniform_f32(g)) : rng_uniform_f64(g);
+    }
+}
+
+cudaError_t launch_rng_draws(uint64_t key, uint32_t const* slot, uint32_t const* sample, uint32_t count, int n_draws,
+                             double* out, cudaStream_t stream)
+{
+    if(count == 0) {
+        return cudaSuccess;
+    }
+    unsigned const threads = 128;
+    rng_draws_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(key, slot, sample, count, n_draws, out);
+    return cudaGetLastError();
+}
+
+} // namespace ptb

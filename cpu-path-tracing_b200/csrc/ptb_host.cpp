@@ -1,0 +1,95 @@
+// ptb_host.cpp -- the entry points of include/ptb200.h that need no GPU: built-in
+// scenes, camera derivation, PPM output.  All of it is host/pt.hpp (the mirror of the
+// reference's scene layer) behind plain pointers.
+#include "../../include/ptb200.h"
+#include "../host/pt.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+extern "C" {
+
+int ptb_abi_version(void)
+{
+    return PTB_ABI_VERSION;
+}
+
+// pt::camera::with_config, /root/reference/src/camera.cpp:3-17
+int ptb_camera_with_config(void const* camera_config, void* camera_out)
+{
+    if(camera_config == nullptr || camera_out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    pt::camera_config cfg{};
+    std::memcpy(static_cast<void*>(&cfg), camera_config, sizeof(cfg));
+    pt::camera const cam = pt::camera::with_config(cfg);
+    std::memcpy(camera_out, static_cast<void const*>(&cam), sizeof(cam));
+    return PTB_OK;
+}
+
+int ptb_builtin_scene(char const* name, int width, int height, void* spheres_out, size_t capacity, size_t* count_out,
+                      void* camera_config_out)
+{
+    if(name == nullptr || width <= 0 || height <= 0) {
+        return PTB_ERR_ARGUMENT;
+    }
+    std::string const which{ name };
+    pt::scene scn{};
+    if(which == "simple") {
+        scn = pt::simple_scene(width, height);
+    }
+    else if(which == "box") {
+        scn = pt::box_scene(width, height);
+    }
+    else if(which == "box_mirror") {
+        scn = pt::box_mirror_scene(width, height);
+    }
+    else if(which == "dof_glass") {
+        scn = pt::dof_glass_scene(width, height);
+    }
+    else if(which == "spheres10k") {
+        scn = pt::spheres10k_scene(width, height);
+    }
+    else {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(count_out != nullptr) {
+        *count_out = scn.spheres.size();
+    }
+    if(camera_config_out != nullptr) {
+        std::memcpy(camera_config_out, static_cast<void const*>(&scn.camera_parameters), sizeof(pt::camera_config));
+    }
+    if(spheres_out != nullptr) {
+        if(capacity < scn.spheres.size()) {
+            return PTB_ERR_ARGUMENT;
+        }
+        std::memcpy(spheres_out, static_cast<void const*>(scn.spheres.data()), sizeof(pt::sphere) * scn.spheres.size());
+    }
+    return PTB_OK;
+}
+
+// Same bytes as the writer of /root/reference/src/main.cpp:240-247: header
+// "P3\n{w} {h}\n255\n", then "{r} {g} {b} " per pixel, no newlines.
+int ptb_write_ppm(char const* path, double const* rgb, int width, int height)
+{
+    if(path == nullptr || rgb == nullptr || width <= 0 || height <= 0) {
+        return PTB_ERR_ARGUMENT;
+    }
+    std::FILE* f = std::fopen(path, "wb");
+    if(f == nullptr) {
+        return PTB_ERR_IO;
+    }
+    std::string buf;
+    buf.reserve(static_cast<size_t>(width) * static_cast<size_t>(height) * 12 + 32);
+    buf += "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
+    size_t const n = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
+    for(size_t i = 0; i < n; ++i) {
+        buf += std::to_string(pt::color_to_int(rgb[i]));
+        buf += ' ';
+    }
+    bool const ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    return (std::fclose(f) == 0 && ok) ? PTB_OK : PTB_ERR_IO;
+}
+
+} // extern "C"

@@ -1,0 +1,85 @@
+// ptb_kernels.h -- host-callable launchers of the CUDA kernels (C++ linkage,
+// internal to libptb200.so; the public surface is include/ptb200.h).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ptb_scene.cuh"
+
+namespace ptb {
+
+// ---- device-resident counters -------------------------------------------------------------
+struct DeviceCounters
+{
+    unsigned long long tile_cursor; // work distribution of the persistent megakernel
+    unsigned long long rays;
+    unsigned long long diffuse;
+    unsigned long long specular;
+    unsigned long long dielectric;
+    unsigned long long paths;
+};
+
+// ---- FP32 throughput path --------------------------------------------------------------------
+struct RenderParamsF32
+{
+    uint64_t key;           // seed_key(seed)
+    uint32_t first_sample;  // absolute index of the first sample of this pass
+    uint32_t samples;       // samples per sub-pixel in this pass
+    uint32_t chunk;         // samples per work tile
+    uint32_t width, height, ns;
+    uint32_t nslots;        // width*height*ns*ns
+    uint32_t ngroups;       // ceil(nslots/32)
+    uint32_t nchunks;       // ceil(samples/chunk)
+    uint32_t ntiles;        // ngroups*nchunks
+    float4* accum;          // [nslots] {sum r, sum g, sum b, n}
+    DeviceCounters* counters;
+    ShadePlanes shade;      // global-memory shading planes
+    GeoLists geo;           // global-memory geometry lists (generic variant)
+    int n_total;
+};
+
+// Copy the packed scene into the constant bank the FP32 kernels read.
+cudaError_t upload_const_scene(ConstSceneF32 const& cs, cudaStream_t stream);
+
+// True when a kernel specialised for (n_small, n_big) exists.
+bool megakernel_has_specialisation(int n_small, int n_big);
+// Launch the persistent megakernel.  grid_blocks = 0 -> SM count * resident blocks.
+cudaError_t launch_megakernel(RenderParamsF32 const& p, int n_small, int n_big, int sm_count, cudaStream_t stream,
+                              int* launches);
+
+struct ProbeParams
+{
+    uint64_t key;
+    uint32_t width, height, ns;
+    uint32_t const* x;
+    uint32_t const* y;
+    uint32_t const* sx;
+    uint32_t const* sy;
+    uint32_t const* sample;
+    uint32_t count;
+    int32_t* primary_hit;
+    double* radiance; // [count*3]
+    double* ray;      // [count*6] or nullptr
+    uint32_t* draws;  // [count] or nullptr
+};
+cudaError_t launch_probe_f32(ProbeParams const& p, ShadePlanes const& shade, GeoLists const& geo, cudaStream_t stream);
+
+// ---- FP64 parity path (reference operation order, no FMA contraction) ----------------------------------
+cudaError_t launch_probe_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam,
+                             cudaStream_t stream);
+cudaError_t launch_render_f64(uint64_t key, uint32_t first_sample, uint32_t samples, uint32_t width, uint32_t height,
+                              uint32_t ns, RawSphere const* spheres, int n, RawCamera const* cam, double* accum64,
+                              DeviceCounters* counters, cudaStream_t stream);
+
+// ---- resolve (main.cpp:181,192-196) -----------------------------------------------------------------------
+// accum32: float4 per slot; accum64: 4 doubles per slot (either may be null, both are summed when present)
+cudaError_t launch_resolve(float4 const* accum32, double const* accum64, uint32_t width, uint32_t height, uint32_t ns,
+                           double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream);
+
+// ---- stream check ---------------------------------------------------------------------------------------------
+cudaError_t launch_rng_draws(uint64_t key, uint32_t const* slot, uint32_t const* sample, uint32_t count, int n_draws,
+                             double* out, cudaStream_t stream);
+
+} // namespace ptb

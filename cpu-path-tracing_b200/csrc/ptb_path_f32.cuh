@@ -1,0 +1,386 @@
+// ptb_path_f32.cuh -- the FP32 throughput arithmetic of one path: camera sample,
+// closest hit, shading, scattering.  Shared by the megakernel, the wavefront
+// kernels and the FP32 probe so that all three trace bit-identical paths.
+//
+// What each piece replaces in the reference (/root/reference/src):
+//   gen_primary   main.cpp:186-190 jitter + camera.cpp:19-38 thin lens (incl. the
+//                 offset = rd*s + rd*t quirk and the un-normalised direction)
+//   closest_hit   main.cpp:30-42 linear scan + sphere.cpp:6-30 quadratic
+//   shade_bounce  main.cpp:115-154 sky / emission / Russian roulette / throughput,
+//                 hit_record.cpp:3-12, diffuse_ray :44-58, specular_ray :60-67,
+//                 dielectric_ray :69-97
+// The draw ORDER of the random stream is the reference's, so a
+// sample consumes the same uniforms here, in the FP64 parity kernels and in the
+// oracle; only the rounding differs.
+#pragma once
+
+#include "ptb_rng.cuh"
+#include "ptb_scene.cuh"
+
+namespace ptb {
+
+constexpr float kEpsilon = 1e-4f;      // constants.hpp:7
+constexpr int kDepthLimit = 100;       // constants.hpp:10
+constexpr int kRouletteThreshold = 4;  // main.cpp:106
+constexpr uint32_t kNoHitBits = 0x7F800000u; // +inf: also what "t < inf" (main.cpp:41) becomes
+
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct PathF32
+{
+    float ox, oy, oz; // ray origin (shifted frame)
+    float dx, dy, dz; // ray direction, NOT normalised (camera.cpp:36)
+    float tr, tg, tb; // accumulated_reflectance (main.cpp:108)
+    float er, eg, eb; // accumulated_emission   (main.cpp:107)
+    Rng rng;
+    int depth;
+};
+
+// slot -> (x, y, sx, sy) in reference loop coordinates; slot = ((y*W+x)*ns+sy)*ns+sx
+__device__ __forceinline__ void slot_coords(uint32_t slot, uint32_t width, uint32_t ns, uint32_t& x, uint32_t& y,
+                                            uint32_t& sx, uint32_t& sy)
+{
+    uint32_t pix;
+    if(ns == 2u) {
+        sx = slot & 1u;
+        sy = (slot >> 1) & 1u;
+        pix = slot >> 2;
+    }
+    else {
+        sx = slot % ns;
+        uint32_t const q = slot / ns;
+        sy = q % ns;
+        pix = q / ns;
+    }
+    y = pix / width;
+    x = pix - y * width;
+}
+
+// main.cpp:186-190 + camera.cpp:19-38
+__device__ __forceinline__ void gen_primary(PathF32& p, CameraF32 const& cam, uint32_t x, uint32_t y, uint32_t sx,
+                                            uint32_t sy)
+{
+    float const len = cam.sub_len;
+    float const u0 = rng_uniform_f32(p.rng);
+    float const u1 = rng_uniform_f32(p.rng);
+    float const xs = (static_cast<float>(x) + static_cast<float>(sx) * len) + len * u0;
+    float const ys = (static_cast<float>(y) + static_cast<float>(sy) * len) + len * u1;
+    float const s = xs * cam.inv_w;
+    float const t = ys * cam.inv_h;
+
+    // rejection-sampled unit disk, x drawn before y (camera.cpp:21-29)
+    float lx, ly;
+    do {
+        lx = fmaf(2.0f, rng_uniform_f32(p.rng), -1.0f);
+        ly = fmaf(2.0f, rng_uniform_f32(p.rng), -1.0f);
+    } while(fmaf(lx, lx, ly * ly) >= 1.0f);
+
+    float const st = s + t; // offset = rd*s + rd*t, z component 0 (camera.cpp:34-35)
+    float const offx = lx * cam.lens_radius * st;
+    float const offy = ly * cam.lens_radius * st;
+
+    p.ox = cam.px + offx;
+    p.oy = cam.py + offy;
+    p.oz = cam.pz;
+    p.dx = fmaf(cam.bx, t, fmaf(cam.ax, s, cam.rx)) - offx;
+    p.dy = fmaf(cam.by, t, fmaf(cam.ay, s, cam.ry)) - offy;
+    p.dz = fmaf(cam.bz, t, fmaf(cam.az, s, cam.rz));
+    p.tr = p.tg = p.tb = 1.0f;
+    p.er = p.eg = p.eb = 0.0f;
+    p.depth = 0;
+}
+
+// Per-ray invariants of the sphere tests (sphere.cpp:9 `a`, plus the expanded terms
+// of the big-sphere form).
+struct RayTerms
+{
+    float a;     // d.d
+    float eps_a; // epsilon * a : roots are compared in units of a*t
+    float od;    // o.d
+    float oo;    // o.o
+    float o2x, o2y, o2z; // 2*o
+};
+
+__device__ __forceinline__ RayTerms ray_terms(PathF32 const& p)
+{
+    RayTerms r;
+    r.a = fmaf(p.dx, p.dx, fmaf(p.dy, p.dy, p.dz * p.dz));
+    r.eps_a = kEpsilon * r.a;
+    r.od = fmaf(p.ox, p.dx, fmaf(p.oy, p.dy, p.oz * p.dz));
+    r.oo = fmaf(p.ox, p.ox, fmaf(p.oy, p.oy, p.oz * p.oz));
+    r.o2x = p.ox + p.ox;
+    r.o2y = p.oy + p.oy;
+    r.o2z = p.oz + p.oz;
+    return r;
+}
+
+// Candidate key of one sphere: bits of (a*t - eps*a) for the smallest root with
+// t >= eps, or something >= 0x7F800000 when there is none.  Non-negative floats
+// order like unsigned integers; negative values (root < eps) and NaN
+// (discriminant < 0, sphere.cpp:14) order ABOVE +inf, so a single unsigned min
+// does "root < eps -> try the far root -> reject" (sphere.cpp:21-27).
+__device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& p, RayTerms const& r)
+{
+    float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz; // c - o = -oc
+    float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));       // -half_b
+    float const cc = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, -s.r2))); // c (sphere.cpp:11)
+    float const disc = fmaf(nb, nb, -(r.a * cc));
+    float const sq = fast_sqrt(disc);
+    float const h = nb - r.eps_a;
+    float const tn = h - sq;
+    float const tf = h + sq;
+    return min(__float_as_uint(tn), __float_as_uint(tf));
+}
+
+__device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, RayTerms const& r)
+{
+    float const hb = fmaf(p.dx, b.gx, fmaf(p.dy, b.gy, fmaf(p.dz, b.gz, b.k * r.od)));           // half_b / 2R
+    float const cp = fmaf(r.o2x, b.gx, fmaf(r.o2y, b.gy, fmaf(r.o2z, b.gz, fmaf(b.k, r.oo, b.K)))); // c / 2R
+    float const ac = r.a * cp;
+    float const disc = fmaf(hb, hb, -(b.k * ac));
+    float const sq = fast_sqrt(disc);
+    float const den = sq - hb;
+    float const tn = fmaf(ac, fast_rcp(den), -r.eps_a); // a*c/(sqrt - hb): no cancellation for the near root
+    float const tf = fmaf(den, b.two_r, -r.eps_a);      // a*(sqrt - hb)/(a k)
+    return min(__float_as_uint(tn), __float_as_uint(tf));
+}
+
+// main.cpp:30-42.  NS/NB >= 0: counts known at compile time, geometry read straight
+// from constant-bank operands, fully unrolled.  NS = NB = -1: run-time counts,
+// geometry from global memory (any scene size).
+template<int NS, int NB>
+__device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists const& gl, PathF32 const& p,
+                                            RayTerms const& r, float& t_out, int& id_out)
+{
+    uint32_t best = kNoHitBits;
+    int id = -1;
+    if constexpr(NS >= 0) {
+#pragma unroll
+        for(int i = 0; i < NS; ++i) {
+            uint32_t const k = key_small(cs.small_geo[i], p, r);
+            if(k < best) {
+                best = k;
+                id = cs.small_id[i];
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < NB; ++i) {
+            uint32_t const k = key_big(cs.big_geo[i], p, r);
+            if(k < best) {
+                best = k;
+                id = cs.big_id[i];
+            }
+        }
+    }
+    else {
+        int const ns = cs.n_small;
+        int const nb = cs.n_big;
+#pragma unroll 4
+        for(int i = 0; i < ns; ++i) {
+            uint32_t const k = key_small(gl.small_geo[i], p, r);
+            if(k < best) {
+                best = k;
+                id = i;
+            }
+        }
+        if(id >= 0) {
+            id = gl.small_id[id];
+        }
+        int idb = -1;
+        for(int i = 0; i < nb; ++i) {
+            uint32_t const k = key_big(gl.big_geo[i], p, r);
+            if(k < best) {
+                best = k;
+                idb = i;
+            }
+        }
+        if(idb >= 0) {
+            id = gl.big_id[idb];
+        }
+    }
+    id_out = id;
+    t_out = (__uint_as_float(best) + r.eps_a) * fast_rcp(r.a);
+    return best < kNoHitBits;
+}
+
+// Primary-hit probe only: same scan, returns the index.
+template<int NS, int NB>
+__device__ __forceinline__ int primary_hit_index(ConstSceneF32 const& cs, GeoLists const& gl, PathF32 const& p)
+{
+    RayTerms const r = ray_terms(p);
+    float t;
+    int id;
+    return closest_hit<NS, NB>(cs, gl, p, r, t, id) ? id : -1;
+}
+
+struct BounceCounters
+{
+    uint32_t rays;
+    uint32_t diffuse;
+    uint32_t specular;
+    uint32_t dielectric;
+};
+
+// specular_ray, main.cpp:60-67: mirror about the OUTWARD normal with the raw
+// direction; the reference then draws one uniform and multiplies it by
+// fuzziness = 0 -- the draw must still advance the stream.
+__device__ __forceinline__ void reflect_ray(PathF32& p, float nx, float ny, float nz)
+{
+    float const dn2 = 2.0f * fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));
+    p.dx = fmaf(-dn2, nx, p.dx);
+    p.dy = fmaf(-dn2, ny, p.dy);
+    p.dz = fmaf(-dn2, nz, p.dz);
+    (void)rng_next32(p.rng);
+}
+
+// One iteration of the bounce loop of main.cpp:111-155 AFTER the closest-hit query.
+// Returns true while the path is alive; on false p.er/eg/eb hold the path's radiance.
+template<bool kCount>
+__device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool hit, float t, int id,
+                                             ShadePlanes const& sp, BounceCounters& cnt)
+{
+    if(!hit) {
+        // main.cpp:116-119 sky gradient on the unit direction
+        float const uy = p.dy * fast_rsqrt(r.a);
+        float const tt = 0.5f * (uy + 1.0f);
+        float const omt = 1.0f - tt;
+        p.er = fmaf(p.tr, fmaf(0.5f, tt, omt), p.er);
+        p.eg = fmaf(p.tg, fmaf(0.7f, tt, omt), p.eg);
+        p.eb = fmaf(p.tb, omt + tt, p.eb);
+        return false;
+    }
+
+    float4 const sa = sp.a[id];
+    float4 const sb = sp.b[id];
+
+    // hit_record.cpp:5-9
+    float const hx = fmaf(p.dx, t, p.ox);
+    float const hy = fmaf(p.dy, t, p.oy);
+    float const hz = fmaf(p.dz, t, p.oz);
+    float const nx = fmaf(hx, sa.w, sa.x); // outward normal (P - c)/R
+    float const ny = fmaf(hy, sa.w, sa.y);
+    float const nz = fmaf(hz, sa.w, sa.z);
+
+    // main.cpp:126
+    p.er = fmaf(p.tr, sb.x, p.er);
+    p.eg = fmaf(p.tg, sb.y, p.eg);
+    p.eb = fmaf(p.tb, sb.z, p.eb);
+
+    // main.cpp:128-139 Russian roulette with p = max(color), survivor weight color/p
+    float4 col;
+    if(p.depth > kRouletteThreshold) {
+        float4 const sc = sp.c[id];
+        if(!(rng_uniform_f32(p.rng) < sc.w)) {
+            return false;
+        }
+        col = sp.d[id];
+    }
+    else {
+        col = sp.c[id];
+    }
+    p.tr *= col.x;
+    p.tg *= col.y;
+    p.tb *= col.z;
+
+    p.ox = hx;
+    p.oy = hy;
+    p.oz = hz;
+
+    int const refl = __float_as_int(sb.w);
+    if(refl == 1) {
+        if(kCount) {
+            cnt.specular++;
+        }
+        reflect_ray(p, nx, ny, nz);
+    }
+    else {
+        float const dn = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));
+        bool const front = dn < 0.0f; // hit_record.cpp:7
+        float const fx = front ? nx : -nx, fy = front ? ny : -ny, fz = front ? nz : -nz;
+        if(refl == 0) {
+            // diffuse_ray, main.cpp:44-58
+            if(kCount) {
+                cnt.diffuse++;
+            }
+            float const u1 = rng_uniform_f32(p.rng);
+            float const u2 = rng_uniform_f32(p.rng);
+            float sphi, cphi;
+            __sincosf(6.283185307179586f * u1, &sphi, &cphi);
+            float const sin_t = fast_sqrt(u2);
+            float const cos_t = fast_sqrt(1.0f - u2);
+            // u = norm((|w.x| > 0.1 ? (0,1,0) : (1,0,0)) x w), v = w x u
+            float ux, uy, uz;
+            if(fabsf(fx) > 0.1f) {
+                float const inv = fast_rsqrt(fmaf(fz, fz, fx * fx));
+                ux = fz * inv;
+                uy = 0.0f;
+                uz = -fx * inv;
+            }
+            else {
+                float const inv = fast_rsqrt(fmaf(fz, fz, fy * fy));
+                ux = 0.0f;
+                uy = -fz * inv;
+                uz = fy * inv;
+            }
+            float const vx = fy * uz - fz * uy;
+            float const vy = fz * ux - fx * uz;
+            float const vz = fx * uy - fy * ux;
+            float const cu = cphi * sin_t, cv = sphi * sin_t;
+            p.dx = fmaf(ux, cu, fmaf(vx, cv, fx * cos_t));
+            p.dy = fmaf(uy, cu, fmaf(vy, cv, fy * cos_t));
+            p.dz = fmaf(uz, cu, fmaf(vz, cv, fz * cos_t));
+        }
+        else {
+            // dielectric_ray, main.cpp:69-97, refraction index 2.0
+            if(kCount) {
+                cnt.dielectric++;
+            }
+            float const ratio = front ? 0.5f : 2.0f;
+            float const inv_len = fast_rsqrt(r.a);
+            float const cos_t = fminf(fabsf(dn) * inv_len, 1.0f); // (-unit_d).normal, the normal faces the ray
+            float const sin_t = fast_sqrt(fmaxf(0.0f, fmaf(-cos_t, cos_t, 1.0f)));
+            bool reflect = ratio * sin_t > 1.0f;
+            if(!reflect) {
+                // Schlick, r0 = ((1-n)/(1+n))^2 = 1/9 for n = 2 and n = 1/2 alike
+                float const m = 1.0f - cos_t;
+                float const m2 = m * m;
+                float const refl_prob = fmaf(8.0f / 9.0f, m2 * m2 * m, 1.0f / 9.0f);
+                reflect = refl_prob > rng_uniform_f32(p.rng);
+            }
+            if(reflect) {
+                reflect_ray(p, nx, ny, nz);
+            }
+            else {
+                float const px = fmaf(fx, cos_t, p.dx * inv_len) * ratio;
+                float const py = fmaf(fy, cos_t, p.dy * inv_len) * ratio;
+                float const pz = fmaf(fz, cos_t, p.dz * inv_len) * ratio;
+                float const par = -fast_sqrt(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
+                p.dx = fmaf(fx, par, px);
+                p.dy = fmaf(fy, par, py);
+                p.dz = fmaf(fz, par, pz);
+            }
+        }
+    }
+
+    p.depth++;
+    return p.depth < kDepthLimit; // main.cpp:111
+}
+
+} // namespace ptb

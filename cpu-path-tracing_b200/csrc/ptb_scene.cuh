@@ -1,0 +1,111 @@
+// ptb_scene.cuh -- device-side scene layout.
+//
+// Input records are the reference's own AoS FP64 structs (pt::sphere 88 B,
+// /root/reference/src/sphere.hpp:10-17; pt::camera 176 B, src/camera.hpp:23-32).
+// The FP64 parity kernels read them as they are.  The FP32 throughput kernels read
+// a host-packed SoA form built once per ptb_upload_scene (ptb_api.cu: pack_scene):
+//
+//   * all positions are translated by -origin_shift (the camera look region) so
+//     FP32 coordinates stay O(scene extent);
+//   * spheres are split into two geometry classes, each tested with the form that
+//     is numerically stable for it in binary32 ("hard parts"):
+//       small : (c, r^2)                       classic oc-form of sphere.cpp:8-12
+//       big   : (g = -k c, k = 1/2R, K = k(c.c - R^2), 2R)
+//               the same quadratic divided by 2R and expanded about the shifted
+//               origin, coefficients computed in FP64 on the host; near root by
+//               the cancellation-free form c'/(s - hb').  Needed for the R = 1e6
+//               "wall" spheres of box_scene.hpp:16-47, where oc.oc - r^2 has no
+//               correct digits in binary32.
+//   * shading data per ORIGINAL sphere index, four float4 planes.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ptb {
+
+constexpr int kMaxConstSpheres = 64; // geometry lists that live in __constant__ memory
+constexpr int kSmemShadeSpheres = 64; // shading planes staged in shared memory
+
+struct RawSphere // == pt::sphere, 88 bytes
+{
+    double radius;
+    double px, py, pz;
+    double er, eg, eb;
+    double cr, cg, cb;
+    int32_t reflection;
+    int32_t pad_;
+};
+static_assert(sizeof(RawSphere) == 88, "pt::sphere layout");
+
+struct RawCamera // == pt::camera, 176 bytes
+{
+    double pos[3];
+    double llc[3];
+    double ax[3];
+    double ay[3];
+    double u[3], v[3], w[3];
+    double lens_radius;
+};
+static_assert(sizeof(RawCamera) == 176, "pt::camera layout");
+
+struct SmallGeo
+{
+    float cx, cy, cz, r2;
+};
+
+struct BigGeo
+{
+    float gx, gy, gz, k; // g = -k*c, k = 1/(2R)
+    float K, two_r, pad0, pad1; // K = k*(c.c - R^2), two_r = 2R
+};
+
+// FP32 camera, positions relative to origin_shift
+struct CameraF32
+{
+    float px, py, pz;    // position
+    float rx, ry, rz;    // lower_left_corner - position
+    float ax, ay, az;    // cam_x_axis
+    float bx, by, bz;    // cam_y_axis
+    float lens_radius;
+    float inv_w, inv_h;  // 1/width, 1/height
+    float sub_len;       // 1/num_subpixels
+};
+
+// Everything the FP32 kernels read through the constant cache.
+struct ConstSceneF32
+{
+    CameraF32 cam;
+    int n_small;
+    int n_big;
+    int n_total;
+    int pad_;
+    SmallGeo small_geo[kMaxConstSpheres];
+    BigGeo big_geo[kMaxConstSpheres];
+    int small_id[kMaxConstSpheres];
+    int big_id[kMaxConstSpheres];
+};
+
+// Shading planes (global memory; staged to shared memory when n <= kSmemShadeSpheres)
+//   a = (-c/R xyz, 1/R)            outward normal = P * a.w + a.xyz
+//   b = (emission rgb, reflection as int bits)
+//   c = (color rgb, p = max(color))
+//   d = (color/p rgb, 0)           Russian-roulette survivor weight, src/main.cpp:131-132
+struct ShadePlanes
+{
+    float4 const* a;
+    float4 const* b;
+    float4 const* c;
+    float4 const* d;
+};
+
+// Geometry lists for scenes too large for constant memory (same records, global memory)
+struct GeoLists
+{
+    SmallGeo const* small_geo;
+    BigGeo const* big_geo;
+    int const* small_id;
+    int const* big_id;
+};
+
+} // namespace ptb

@@ -1,0 +1,172 @@
+/* ptb200.h -- C ABI of the B200-native per-pixel render loop.
+ *
+ * The reference (AlexandruIca/cpu-path-tracing) has no plugin/FFI boundary: its
+ * hot path is the body of main() between scene construction and PPM output,
+ * src/main.cpp:214-236 (one taskflow task per image row, each calling
+ * render_subpixel -> camera::get_ray -> radiance -> intersect).  This header IS
+ * that boundary, cut so that a host program keeps building pt::scene /
+ * pt::sphere / pt::camera exactly as the reference does and hands plain pointers
+ * across.  Nothing here mentions torch, CUDA types or C++ types.
+ *
+ * Record layouts accepted (the reference's own, little-endian, FP64):
+ *   sphere  : 88 bytes  radius@0 position@8 emission@32 color@56 reflection:int32@80
+ *             = pt::sphere (src/sphere.hpp:10-17) = sandbox Sphere (sandbox/main.cpp:62-66)
+ *   camera  : 176 bytes position@0 lower_left_corner@24 cam_x_axis@48 cam_y_axis@72
+ *             u@96 v@120 w@144 lens_radius@168 = pt::camera (src/camera.hpp:23-32)
+ *   config  : 112 bytes = pt::camera_config (src/camera.hpp:11-21)
+ *
+ * Conventions: every call returns 0 on success or a negative ptb_status; nothing
+ * throws across the boundary; the caller owns every host buffer it passes; the
+ * library owns all device memory behind the opaque context.  A context is bound
+ * to ONE GPU and is not thread-safe (one process / one host thread per GPU, as
+ * under torchrun).  There is NO CPU fallback: without a usable CUDA device
+ * ptb_create fails with PTB_ERR_NO_DEVICE.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1
+
+#define PTB_SPHERE_BYTES 88
+#define PTB_CAMERA_BYTES 176
+#define PTB_CAMERA_CONFIG_BYTES 112
+
+typedef struct ptb_context ptb_context;
+
+typedef enum ptb_status
+{
+    PTB_OK = 0,
+    PTB_ERR_ARGUMENT = -1,  /* null pointer, bad size, bad stride, bad flag */
+    PTB_ERR_NO_DEVICE = -2, /* no CUDA device / device index out of range */
+    PTB_ERR_CUDA = -3,      /* a CUDA runtime call failed; see ptb_last_error */
+    PTB_ERR_STATE = -4,     /* call order: scene / camera / image not set yet */
+    PTB_ERR_IO = -5         /* file output failed */
+} ptb_status;
+
+/* ptb_render flags */
+enum
+{
+    /* integrator variant */
+    PTB_VARIANT_MEGAKERNEL = 0x0, /* one persistent kernel, path regeneration in place */
+    PTB_VARIANT_WAVEFRONT = 0x1,  /* queue-based: generate / intersect / shade-by-material */
+    PTB_VARIANT_MASK = 0xF,
+    /* arithmetic */
+    PTB_PRECISION_FP32 = 0x00, /* throughput mode (the measured mode) */
+    PTB_PRECISION_FP64 = 0x10, /* deterministic parity mode: FP64, no FMA contraction,
+                                  reference operation order */
+    PTB_PRECISION_MASK = 0xF0
+};
+
+typedef struct ptb_stats
+{
+    uint64_t paths;          /* camera samples traced since the last ptb_clear (src/main.cpp:184) */
+    uint64_t rays;           /* closest-hit queries (calls of intersect, src/main.cpp:30) */
+    double last_render_ms;   /* device time of the last ptb_render (CUDA events on its stream) */
+    double total_render_ms;  /* sum of the above since the last ptb_clear */
+    uint64_t kernel_launches; /* kernels launched by this context since creation */
+    uint64_t hits_diffuse;   /* scatter events by material since the last ptb_clear */
+    uint64_t hits_specular;
+    uint64_t hits_dielectric;
+} ptb_stats;
+
+/* ---- library ----------------------------------------------------------------- */
+int ptb_abi_version(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+int ptb_device_count(void);
+/* Message for the last failing call on `ctx` (or of ptb_create when ctx is NULL). */
+char const* ptb_last_error(ptb_context const* ctx);
+
+/* ---- context ----------------------------------------------------------------- */
+/* Replaces tf::Executor / tf::Taskflow construction, src/main.cpp:214-215. */
+int ptb_create(int device, ptb_context** out);
+void ptb_destroy(ptb_context* ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the
+ * stream a framework is recording events on.  NULL = the context's own stream. */
+int ptb_set_stream(ptb_context* ctx, void* cuda_stream);
+int ptb_synchronize(ptb_context* ctx);
+
+/* ---- inputs ------------------------------------------------------------------ */
+/* The sphere list of pt::scene (src/scene.hpp:12-16), in index order (the
+ * closest-hit tie rule of src/main.cpp:35 depends on it).  `stride` >= 88. */
+int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t stride);
+/* A derived pt::camera, i.e. the result of pt::camera::with_config (src/main.cpp:209). */
+int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes);
+/* Image geometry: width/height of src/main.cpp:204-205, num_subpixels of :202.
+ * (Re)allocates and zeroes the accumulation buffer: one float4 {r,g,b,n} of
+ * un-clamped radiance SUMS per sub-pixel (slot = ((y*W+x)*ns+sy)*ns+sx). */
+int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels);
+/* Zero the accumulation buffer and the statistics. */
+int ptb_clear(ptb_context* ctx);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+/* Replaces executor.run(taskflow).wait(), src/main.cpp:217-236: traces samples
+ * [first_sample, first_sample + samples_per_subpixel) of EVERY sub-pixel (the `s`
+ * loop of src/main.cpp:184) and adds their radiance into the accumulation buffer.
+ * Progressive: call again with the next sample range to refine; ranks of a
+ * multi-GPU job call it with disjoint ranges.  Blocks until the device is done.
+ * `seed` keys the counter-based stream (oracle/ptb_rng.h) that replaces the
+ * reference's unseedable per-row mt19937 (src/random_state.cpp:3-7). */
+int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t samples_per_subpixel, uint32_t flags);
+
+/* Per-sub-pixel mean -> clamp to [0,1] -> average of the ns*ns strata, written at
+ * the vertically flipped row: src/main.cpp:181,192-196.  rgb_out: width*height*3
+ * doubles, the layout of the reference's std::vector<pt::vec3> image (main.cpp:210). */
+int ptb_resolve(ptb_context* ctx, double* rgb_out);
+/* Same, straight to 8-bit gamma-2.2 values as pt::color_to_int (src/utils.cpp:11-16):
+ * width*height*3 bytes. */
+int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out);
+
+/* ---- multi-GPU plumbing ------------------------------------------------------------- */
+/* Device address and size of the FP32 accumulation buffer, so that the caller's
+ * collective layer (torch.distributed / NCCL) can sum it across ranks in place
+ * before ptb_resolve on the root.  Slots carry their own sample count in .w, so
+ * a plain sum-reduce is all that is needed. */
+int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes);
+/* Render into / resolve from a caller-owned device buffer (e.g. a torch tensor)
+ * of at least width*height*ns*ns*16 bytes.  NULL returns to the internal one. */
+int ptb_set_accum_buffer(ptb_context* ctx, void* device_ptr, size_t bytes);
+/* Host copy of the accumulation buffer (float4 per slot). */
+int ptb_download_accum(ptb_context* ctx, float* out, size_t floats);
+
+/* ---- introspection ------------------------------------------------------------------ */
+int ptb_get_stats(ptb_context* ctx, ptb_stats* out);
+
+/* Parity probe: trace `count` individual samples (x, y, sx, sy, sample index in
+ * reference loop coordinates) and return, per sample, the sphere index hit by the
+ * camera ray (-1 = miss) and the radiance estimate.  PTB_PRECISION_FP64 gives the
+ * deterministic mode; PTB_PRECISION_FP32 runs the throughput kernels' arithmetic.
+ * radiance_out: count*3 doubles.  ray_out (optional): count*6 doubles origin+direction.
+ * draws_out (optional): random draws consumed per sample. */
+int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,
+                      uint32_t const* sy, uint32_t const* sample, size_t count, uint32_t flags, int32_t* primary_hit_out,
+                      double* radiance_out, double* ray_out, uint32_t* draws_out);
+
+/* Raw uniforms of the counter stream for (seed, slot, sample): draws_out[count*n_draws]
+ * as doubles, generated ON THE DEVICE.  For checking the stream against oracle/ptb_rng.h. */
+int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_t const* sample, size_t count,
+                  int n_draws, double* draws_out);
+
+/* ---- host-side helpers mirroring the reference's scene layer (no GPU needed) ----------------- */
+/* pt::camera::with_config (src/camera.cpp:3-17): 112-byte config -> 176-byte camera. */
+int ptb_camera_with_config(void const* camera_config, void* camera_out);
+/* Built-in scenes: "simple" (src/simple_scene.hpp:14-52), "box" (src/box_scene.hpp:14-72),
+ * "box_mirror" (src/box_mirror_scene.hpp:14-72), "dof_glass" (BASELINE config 4),
+ * "spheres10k" (config 5).  Writes up to `capacity` 88-byte spheres, the
+ * count, and the 112-byte camera_config.  Call with spheres_out = NULL to query the count. */
+int ptb_builtin_scene(char const* name, int width, int height, void* spheres_out, size_t capacity, size_t* count_out,
+                      void* camera_config_out);
+/* ASCII PPM "P3" writer with gamma 2.2, byte-compatible with src/main.cpp:240-247. */
+int ptb_write_ppm(char const* path, double const* rgb, int width, int height);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PTB200_H */
