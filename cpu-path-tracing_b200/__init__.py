@@ -25,7 +25,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libptb200.so")
+LIB_PATH = os.environ.get("PTB200_LIB", os.path.join(HERE, "libptb200.so"))  # override: development A/B builds only
 
 SPHERE_BYTES = 88
 CAMERA_BYTES = 176

@@ -828,7 +828,8 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
     }
     else {
         PTB_CUDA_T(upload_const_scene(ctx->cs, st));
-        PTB_CUDA_T(launch_probe_f32(q, shade_planes(ctx), geo_lists(ctx), st));
+        int const ns_spec = ctx->n_small <= kMaxConstSpheres && ctx->n_big <= kMaxConstSpheres ? ctx->n_small : -1;
+        PTB_CUDA_T(launch_probe_f32(q, ns_spec, ctx->n_big, shade_planes(ctx), geo_lists(ctx), st));
     }
     ctx->stats.kernel_launches += 1;
     PTB_CUDA_T(cudaMemcpyAsync(primary_hit_out, d_hit, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -8,10 +8,11 @@
 //     (32 consecutive sub-pixel slots x `chunk` samples) from one global cursor, so
 //     the tail of the launch is one tile, not one wave;
 //   * inside a tile the 32 lanes share a pool of (slot, sample) items.  A lane whose
-//     path ended takes the next item of the pool at the top of the loop ("path
-//     regeneration"), so the closest-hit scan -- >80 % of the instructions -- always
+//     path ended takes the next ready camera sample at the top of the loop ("path
+//     regeneration"), so the closest-hit scan -- the bulk of the instructions -- always
 //     runs with every lane busy, whatever the spread of path lengths (geometric,
-//     mean 12.3 bounces, limit 100 in the box scenes);
+//     mean 12.3 bounces, limit 100 in the box scenes).  Camera samples are generated
+//     32 at a time, by all lanes together, into a per-warp shared-memory ring;
 //   * the random stream is keyed by (seed, slot, sample), so which lane traces which
 //     item does not change the image;
 //   * sphere geometry is read as constant-bank operands of the FFMA/FADD
@@ -47,10 +48,25 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
     return __reduce_add_sync(0xffffffffu, v);
 }
 
+// Per-warp ring of pre-generated camera samples (shared memory).  Generating a primary ray
+// costs ~130 instructions; done in place by the one or two lanes whose path just ended it
+// would issue at <10 % lane utilisation on almost every iteration (measured: 30 % of all
+// issue slots, profiles/r1_mega_v1_*).  Instead ALL 32 lanes generate one sample each when
+// the ring runs low (full lane utilisation, once per ~12 iterations) and a lane whose
+// path ended just pops a ready ray: two 16-byte shared loads.
+constexpr int kRingSize = 64; // entries per warp, power of two, >= 2 * 32
+struct WarpRing
+{
+    float4 a[kRingSize]; // ox, oy, dx, dy
+    float4 b[kRingSize]; // dz, rng.state, rng.inc, slot (bits); oz is the camera's z (lens offset has no z)
+};
+constexpr uint32_t kVoidSlot = 0xFFFFFFFFu;
+
 template<int NS, int NB, bool kSmemShade>
 __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 const prm)
 {
     __shared__ float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
+    __shared__ WarpRing s_ring[kMegaThreads / 32];
     ShadePlanes sp = prm.shade;
     if constexpr(kSmemShade) {
         for(int i = threadIdx.x; i < prm.n_total; i += kMegaThreads) {
@@ -68,10 +84,14 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
 
     uint32_t const lane = threadIdx.x & 31u;
     uint32_t const lt_mask = (1u << lane) - 1u;
+    WarpRing& ring = s_ring[threadIdx.x >> 5];
 
-    // warp-uniform tile state
-    uint32_t tile_slot0 = 0, tile_sample0 = 0, tile_items = 0, next_item = 0;
+    // warp-uniform state: current work tile and ring occupancy
+    uint32_t tile_sample0 = 0, tile_samples = 0, next_sample = 0;
+    uint32_t ring_head = 0, ring_tail = 0, ring_count = 0;
     bool exhausted = false;
+    // per-lane: the sub-pixel this lane GENERATES for in the current tile
+    uint32_t gen_slot = kVoidSlot, gen_x = 0, gen_y = 0, gen_sx = 0, gen_sy = 0;
 
     bool alive = false;
     uint32_t slot = 0;
@@ -79,9 +99,9 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
     BounceCounters cnt{ 0, 0, 0, 0 };
 
     for(;;) {
-        uint32_t const need = __ballot_sync(0xffffffffu, !alive);
-        if(need != 0u && !exhausted) {
-            if(next_item >= tile_items) {
+        // ---- refill: every lane generates one camera sample --------------------------------
+        if(ring_count <= kRingSize - 32 && !exhausted) {
+            if(next_sample >= tile_samples) {
                 unsigned long long t = 0;
                 if(lane == 0) {
                     t = atomicAdd(&prm.counters->tile_cursor, 1ull);
@@ -94,34 +114,75 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                     uint32_t const tile = static_cast<uint32_t>(t);
                     uint32_t const group = tile / prm.nchunks;
                     uint32_t const chunk = tile - group * prm.nchunks;
-                    tile_slot0 = group * 32u;
                     tile_sample0 = chunk * prm.chunk;
-                    tile_items = 32u * min(prm.chunk, prm.samples - tile_sample0);
-                    next_item = 0;
+                    tile_samples = min(prm.chunk, prm.samples - tile_sample0);
+                    next_sample = 0;
+                    gen_slot = group * 32u + lane;
+                    if(gen_slot < prm.nslots) {
+                        slot_coords(gen_slot, prm.width, prm.ns, gen_x, gen_y, gen_sx, gen_sy);
+                    }
+                    else {
+                        gen_slot = kVoidSlot;
+                    }
                 }
             }
             if(!exhausted) {
-                uint32_t const my = next_item + __popc(need & lt_mask);
-                if(!alive && my < tile_items) {
-                    slot = tile_slot0 + (my & 31u);
-                    if(slot < prm.nslots) {
-                        uint32_t const sample = prm.first_sample + tile_sample0 + (my >> 5);
-                        p.rng = rng_open(prm.key, slot, sample);
-                        uint32_t x, y, sx, sy;
-                        slot_coords(slot, prm.width, prm.ns, x, y, sx, sy);
-                        gen_primary(p, c_scene.cam, x, y, sx, sy);
-                        alive = true;
-                    }
+                PathF32 g;
+                g.dx = g.dy = g.dz = g.ox = g.oy = 0.0f;
+                g.rng.state = g.rng.inc = 0u;
+                if(gen_slot != kVoidSlot) {
+                    g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
+                    gen_primary(g, c_scene.cam, gen_x, gen_y, gen_sx, gen_sy);
                 }
-                next_item += __popc(need);
+                uint32_t const w = (ring_head + lane) & (kRingSize - 1);
+                ring.a[w] = make_float4(g.ox, g.oy, g.dx, g.dy);
+                ring.b[w] = make_float4(g.dz, __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc),
+                                        __uint_as_float(gen_slot));
+                ring_head = (ring_head + 32u) & (kRingSize - 1);
+                ring_count += 32u;
+                next_sample += 1u;
+                __syncwarp();
             }
         }
+
+        // ---- lanes whose path ended pop a ready sample ----------------------------------------
+        uint32_t const need = __ballot_sync(0xffffffffu, !alive);
+        if(need != 0u && ring_count != 0u) {
+            uint32_t const rank = __popc(need & lt_mask);
+            if(!alive && rank < ring_count) {
+                uint32_t const rd = (ring_tail + rank) & (kRingSize - 1);
+                float4 const ea = ring.a[rd];
+                float4 const eb = ring.b[rd];
+                slot = __float_as_uint(eb.w);
+                if(slot != kVoidSlot) {
+                    p.ox = ea.x;
+                    p.oy = ea.y;
+                    p.oz = c_scene.cam.pz;
+                    p.dx = ea.z;
+                    p.dy = ea.w;
+                    p.dz = eb.x;
+                    p.rng.state = __float_as_uint(eb.y);
+                    p.rng.inc = __float_as_uint(eb.z);
+                    p.tr = p.tg = p.tb = 1.0f;
+                    p.er = p.eg = p.eb = 0.0f;
+                    p.depth = 0;
+                    alive = true;
+                }
+            }
+            uint32_t const taken = min(static_cast<uint32_t>(__popc(need)), ring_count);
+            ring_tail = (ring_tail + taken) & (kRingSize - 1);
+            ring_count -= taken;
+            __syncwarp();
+        }
+
         if(!__any_sync(0xffffffffu, alive)) {
-            if(exhausted) {
+            if(exhausted && ring_count == 0u) {
                 break;
             }
             continue;
         }
+
+        // ---- one bounce ---------------------------------------------------------------------------
         if(alive) {
             RayTerms const r = ray_terms(p);
             float t;
@@ -217,7 +278,9 @@ cudaError_t launch_megakernel(RenderParamsF32 const& p, int n_small, int n_big, 
 }
 
 // ---- FP32 probe ---------------------------------------------------------------------------------
-// One thread per requested sample; same device functions as the megakernel.
+// One thread per requested sample; same device functions AND the same (n_small, n_big)
+// specialisation as the megakernel, so the probe traces what the renderer traces.
+template<int NS, int NB>
 __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoLists const geo)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,6 +291,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
     uint32_t const slot = ((y * q.width + x) * q.ns + sy) * q.ns + sx;
     PathF32 p;
     p.rng = rng_open(q.key, slot, q.sample[i]);
+    p.oz = c_scene.cam.pz;
     gen_primary(p, c_scene.cam, x, y, sx, sy);
     if(q.ray != nullptr) {
         q.ray[6 * i + 0] = p.ox;
@@ -237,7 +301,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         q.ray[6 * i + 4] = p.dy;
         q.ray[6 * i + 5] = p.dz;
     }
-    q.primary_hit[i] = primary_hit_index<-1, -1>(c_scene, geo, p);
+    q.primary_hit[i] = primary_hit_index<NS, NB>(c_scene, geo, p);
 
     BounceCounters cnt{ 0, 0, 0, 0 };
     bool alive = true;
@@ -245,7 +309,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         RayTerms const r = ray_terms(p);
         float t;
         int id;
-        bool const hit = closest_hit<-1, -1>(c_scene, geo, p, r, t, id);
+        bool const hit = closest_hit<NS, NB>(c_scene, geo, p, r, t, id);
         alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
     }
     q.radiance[3 * i + 0] = p.er;
@@ -256,14 +320,22 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
     }
 }
 
-cudaError_t launch_probe_f32(ProbeParams const& p, ShadePlanes const& shade, GeoLists const& geo, cudaStream_t stream)
+cudaError_t launch_probe_f32(ProbeParams const& p, int n_small, int n_big, ShadePlanes const& shade, GeoLists const& geo,
+                             cudaStream_t stream)
 {
     if(p.count == 0) {
         return cudaSuccess;
     }
     unsigned const threads = 128;
     unsigned const blocks = (p.count + threads - 1) / threads;
-    probe_f32_kernel<<<blocks, threads, 0, stream>>>(p, shade, geo);
+#define X(a, b) \
+    if(n_small == (a) && n_big == (b)) { \
+        probe_f32_kernel<(a), (b)><<<blocks, threads, 0, stream>>>(p, shade, geo); \
+        return cudaGetLastError(); \
+    }
+    PTB_MEGA_SPECIALISATIONS(X)
+#undef X
+    probe_f32_kernel<-1, -1><<<blocks, threads, 0, stream>>>(p, shade, geo);
     return cudaGetLastError();
 }
 

