@@ -97,6 +97,8 @@ _ptb_clear = _sig("ptb_clear", ctypes.c_int, _vp)
 _ptb_render = _sig("ptb_render", ctypes.c_int, _vp, _u64, _u32, _u32, _u32)
 _ptb_resolve = _sig("ptb_resolve", ctypes.c_int, _vp, _vp)
 _ptb_resolve_rgb8 = _sig("ptb_resolve_rgb8", ctypes.c_int, _vp, _vp)
+_ptb_resolve_device = _sig("ptb_resolve_device", ctypes.c_int, _vp, ctypes.POINTER(_vp))
+_ptb_measure_fp32_peak = _sig("ptb_measure_fp32_peak", ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_double))
 _ptb_accum_buffer = _sig("ptb_accum_buffer", ctypes.c_int, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz))
 _ptb_set_accum_buffer = _sig("ptb_set_accum_buffer", ctypes.c_int, _vp, _vp, _sz)
 _ptb_download_accum = _sig("ptb_download_accum", ctypes.c_int, _vp, _vp, _sz)
@@ -113,7 +115,7 @@ _ptb_write_ppm = _sig("ptb_write_ppm", ctypes.c_int, ctypes.c_char_p, _vp, ctype
 EXPORTED_SYMBOLS = (
     "ptb_abi_version", "ptb_device_count", "ptb_last_error", "ptb_create", "ptb_destroy", "ptb_set_stream",
     "ptb_synchronize", "ptb_upload_scene", "ptb_set_camera", "ptb_set_image", "ptb_clear", "ptb_render",
-    "ptb_resolve", "ptb_resolve_rgb8", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
+    "ptb_resolve", "ptb_resolve_rgb8", "ptb_resolve_device", "ptb_measure_fp32_peak", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
     "ptb_get_stats", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
     "ptb_write_ppm",
 )
@@ -265,6 +267,18 @@ class Renderer:
         out = np.empty((self.height, self.width, 3), dtype=np.uint8)
         self._check(_ptb_resolve_rgb8(self._ctx, _ptr(out)))
         return out
+
+    def resolve_device(self) -> int:
+        """Resolve without leaving the GPU; returns the device address of the W*H*3 FP64 image."""
+        p = _vp(None)
+        self._check(_ptb_resolve_device(self._ctx, ctypes.byref(p)))
+        return p.value
+
+    def measure_fp32_peak(self) -> float:
+        """Measured FFMA rate of this GPU in TFLOP/s (the FP32 roofline denominator)."""
+        v = ctypes.c_double(0.0)
+        self._check(_ptb_measure_fp32_peak(self._ctx, ctypes.byref(v)))
+        return v.value
 
     # -- multi-GPU plumbing
     def accum_buffer(self):

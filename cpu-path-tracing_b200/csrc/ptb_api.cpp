@@ -680,6 +680,65 @@ int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out)
     return resolve_common(ctx, nullptr, rgb8_out);
 }
 
+int ptb_resolve_device(ptb_context* ctx, void** device_rgb)
+{
+    int rc = require_ready(ctx, true);
+    if(rc != PTB_OK) {
+        return rc;
+    }
+    if(device_rgb == nullptr) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_resolve_device: output pointer is null");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, launch_resolve(active_accum(ctx), ctx->accum64_used ? ctx->d_accum64 : nullptr,
+                                 static_cast<uint32_t>(ctx->width), static_cast<uint32_t>(ctx->height),
+                                 static_cast<uint32_t>(ctx->ns), ctx->d_rgb, nullptr, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *device_rgb = ctx->d_rgb;
+    return PTB_OK;
+}
+
+int ptb_measure_fp32_peak(ptb_context* ctx, double* tflops_out)
+{
+    if(ctx == nullptr || tflops_out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    float* scratch = nullptr;
+    PTB_CUDA(ctx, cudaMalloc(&scratch, sizeof(float)));
+    cudaStream_t const st = ctx->stream;
+    double flop = 0.0;
+    double best_ms = 1e30;
+    cudaError_t e = launch_fp32_peak(ctx->sm_count, 256, scratch, st, &flop); // warm-up
+    for(int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {
+        e = cudaEventRecord(ctx->ev0, st);
+        if(e == cudaSuccess) {
+            e = launch_fp32_peak(ctx->sm_count, 4096, scratch, st, &flop);
+        }
+        if(e == cudaSuccess) {
+            e = cudaEventRecord(ctx->ev1, st);
+        }
+        if(e == cudaSuccess) {
+            e = cudaStreamSynchronize(st);
+        }
+        float ms = 0.0f;
+        if(e == cudaSuccess) {
+            e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        }
+        if(e == cudaSuccess && ms < best_ms) {
+            best_ms = ms;
+        }
+    }
+    cudaFree(scratch);
+    ctx->stats.kernel_launches += 6;
+    if(e != cudaSuccess) {
+        return fail_cuda(ctx, e, "ptb_measure_fp32_peak");
+    }
+    *tflops_out = flop / (best_ms * 1e-3) * 1e-12;
+    return PTB_OK;
+}
+
 int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes)
 {
     if(ctx == nullptr || device_ptr == nullptr || bytes == nullptr) {

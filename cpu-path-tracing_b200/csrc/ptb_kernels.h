@@ -79,6 +79,9 @@ cudaError_t launch_render_f64(uint64_t key, uint32_t first_sample, uint32_t samp
 cudaError_t launch_resolve(float4 const* accum32, double const* accum64, uint32_t width, uint32_t height, uint32_t ns,
                            double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream);
 
+// ---- FP32 peak calibration (FFMA loop) ------------------------------------------------------------------------
+cudaError_t launch_fp32_peak(int sm_count, int iters, float* scratch, cudaStream_t stream, double* flop_out);
+
 // ---- stream check ---------------------------------------------------------------------------------------------
 cudaError_t launch_rng_draws(uint64_t key, uint32_t const* slot, uint32_t const* sample, uint32_t count, int n_draws,
                              double* out, cudaStream_t stream);

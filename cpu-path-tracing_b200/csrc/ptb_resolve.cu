@@ -67,6 +67,35 @@ __global__ void resolve_kernel(float4 const* __restrict__ accum32, double const*
 
 } // namespace
 
+// FP32 roofline calibration: 8 independent FFMA chains per thread, 2048 threads per SM.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed)
+{
+    float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
+          a7 = a0 + 7.f;
+    float const b = seed * 0.5f, c = seed * 0.25f;
+    for(int it = 0; it < iters; ++it) {
+#pragma unroll
+        for(int u = 0; u < 8; ++u) {
+            asm volatile("fma.rn.f32 %0, %0, %8, %9; fma.rn.f32 %1, %1, %8, %9; fma.rn.f32 %2, %2, %8, %9; fma.rn.f32 %3, %3, %8, %9;"
+                         "fma.rn.f32 %4, %4, %8, %9; fma.rn.f32 %5, %5, %8, %9; fma.rn.f32 %6, %6, %8, %9; fma.rn.f32 %7, %7, %8, %9;"
+                         : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3), "+f"(a4), "+f"(a5), "+f"(a6), "+f"(a7)
+                         : "f"(b), "f"(c));
+        }
+    }
+    float const r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if(r == 123.456f) {
+        out[0] = r;
+    }
+}
+
+cudaError_t launch_fp32_peak(int sm_count, int iters, float* scratch, cudaStream_t stream, double* flop_out)
+{
+    int const grid = sm_count * 8;
+    fp32_peak_kernel<<<grid, 256, 0, stream>>>(scratch, iters, 1.0f);
+    *flop_out = static_cast<double>(grid) * 256.0 * static_cast<double>(iters) * 64.0 * 2.0;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(float4 const* accum32, double const* accum64, uint32_t width, uint32_t height, uint32_t ns,
                            double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream)
 {

@@ -123,6 +123,10 @@ int ptb_resolve(ptb_context* ctx, double* rgb_out);
  * width*height*3 bytes. */
 int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out);
 
+/* Resolve on the device only: *device_rgb receives the address of width*height*3 doubles
+ * owned by the context (valid until the next ptb_set_image / ptb_destroy).  No copy. */
+int ptb_resolve_device(ptb_context* ctx, void** device_rgb);
+
 /* ---- multi-GPU plumbing ------------------------------------------------------------- */
 /* Device address and size of the FP32 accumulation buffer, so that the caller's
  * collective layer (torch.distributed / NCCL) can sum it across ranks in place
@@ -152,6 +156,11 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
  * as doubles, generated ON THE DEVICE.  For checking the stream against oracle/ptb_rng.h. */
 int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_t const* sample, size_t count,
                   int n_draws, double* draws_out);
+
+/* Roofline calibration: runs a dependent-free FFMA loop on every SM of the context's GPU
+ * and reports the achieved FP32 rate in TFLOP/s (FFMA = 2 flop).  This is the measured
+ * denominator of the FP32-issue roofline the render loop is bound by. */
+int ptb_measure_fp32_peak(ptb_context* ctx, double* tflops_out);
 
 /* ---- host-side helpers mirroring the reference's scene layer (no GPU needed) ----------------- */
 /* pt::camera::with_config (src/camera.cpp:3-17): 112-byte config -> 176-byte camera. */

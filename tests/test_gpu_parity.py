@@ -1,0 +1,351 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes over libptb200.so).
+
+Bars (BASELINE.json north_star):
+  (a) deterministic mode (PTB_PRECISION_FP64): primary-ray hit sphere indices BIT-EXACT, per-sample
+      radiance within 1e-4 relative;
+  (b) throughput mode (FP32 megakernel): images statistically matching at matched spp.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_renderer
+
+pytestmark = pytest.mark.gpu
+
+SCENES = ("simple", "box", "box_mirror", "dof_glass")
+REL_TOL = 1e-4  # north_star: "per-sample radiance matches within 1e-4 relative"
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-12)
+
+
+def probe_inputs(rng, W, H, n, nsub=2, smax=1 << 24):
+    return (rng.integers(0, W, n), rng.integers(0, H, n), rng.integers(0, nsub, n), rng.integers(0, nsub, n),
+            rng.integers(0, smax, n))
+
+
+# ---- (a) deterministic mode ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["simple", "box", "box_mirror"])
+def test_fp64_samples_against_reference_golden(gpu, golden, golden_scene, name):
+    """The committed vectors come from the reference's own intersect()/radiance() (tests/golden/make_golden.py)."""
+    z = golden(f"samples_{name}.npz")
+    W, H = int(z["width"]), int(z["height"])
+    sph, _, cam = golden_scene(name, W, H)
+    with make_renderer(gpu, sph, cam, W, H, int(z["nsub"])) as r:
+        hit, rad, ray, draws = r.trace_samples(int(z["seed"]), z["x"], z["y"], z["sx"], z["sy"], z["sample"],
+                                               gpu.PRECISION_FP64)
+    assert np.array_equal(hit, z["hit"]), "primary-hit indices must be bit-exact"
+    assert np.array_equal(ray, z["ray"]), "camera rays use only + - * / sqrt: bit-exact"
+    rel = rel_err(rad, z["radiance"])
+    assert (rel <= REL_TOL).mean() >= 0.999, f"{(rel > REL_TOL).sum()} of {len(rel)} samples off by more than {REL_TOL}"
+    assert (draws == z["draws"]).mean() >= 0.999
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fp64_samples_against_oracle(gpu, oracle_port, name):
+    rng = np.random.default_rng(7)
+    W, H, n = 333, 187, 50000  # odd sizes on purpose
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, n)
+    ohit, orad, oray, odraws = oracle_port.samples(sph, cam, W, H, 2, 99, xs, ys, sx, sy, ss)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        hit, rad, ray, draws = r.trace_samples(99, xs, ys, sx, sy, ss, gpu.PRECISION_FP64)
+    assert np.array_equal(hit, ohit)
+    assert np.array_equal(ray, oray)
+    rel = rel_err(rad, orad)
+    assert (rel <= REL_TOL).mean() >= 0.999
+    # mirror-only paths touch nothing but + - * / sqrt: most samples are bit-identical
+    assert (rad == orad).all(axis=1).mean() > 0.9
+    assert (draws == odraws).mean() >= 0.999
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fp64_image_against_oracle(gpu, oracle_port, name):
+    W, H, S = 96, 54, 6
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    ref = oracle_port.render(sph, cam, W, H, S, 2, 5, 0)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(5, 0, S, gpu.PRECISION_FP64)
+        img = r.resolve()
+        st = r.stats()
+    assert st.paths == W * H * 4 * S
+    # a handful of chaotic paths may differ (sin/cos/pow ulps): everything else agrees to rounding
+    close = np.abs(img - ref) <= 1e-9
+    assert close.mean() >= 0.998
+    assert np.abs(img - ref).mean() < 1e-4
+
+
+def test_fp64_image_against_reference_golden(gpu, golden):
+    for name in ("simple", "box", "box_mirror"):
+        z = golden(f"image_{name}.npz")
+        w, h, S = int(z["width"]), int(z["height"]), int(z["samps"])
+        sph, cfg = gpu.builtin_scene(name, w, h)
+        cam = gpu.camera_with_config(cfg)
+        with make_renderer(gpu, sph, cam, w, h, int(z["nsub"])) as r:
+            r.render(int(z["seed"]), int(z["first_sample"]), S, gpu.PRECISION_FP64)
+            img = r.resolve()
+        assert (np.abs(img - z["image"]) <= 1e-9).mean() >= 0.998
+
+
+def test_nsub_other_than_two(gpu, oracle_port):
+    for nsub in (1, 3):
+        W, H, S = 40, 30, 3
+        sph, cfg = gpu.builtin_scene("box", W, H)
+        cam = gpu.camera_with_config(cfg)
+        ref = oracle_port.render(sph, cam, W, H, S, nsub, 8, 0)
+        with make_renderer(gpu, sph, cam, W, H, nsub) as r:
+            r.render(8, 0, S, gpu.PRECISION_FP64)
+            img64 = r.resolve()
+            r.clear()
+            r.render(8, 0, S, gpu.PRECISION_FP32)
+            img32 = r.resolve()
+        assert (np.abs(img64 - ref) <= 1e-9).mean() >= 0.995
+        assert np.abs(img32 - ref).mean() < 5e-3
+
+
+# ---- (b) throughput mode -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SCENES)
+def test_fp32_samples_against_oracle(gpu, oracle_port, name):
+    """Same uniforms, FP32 arithmetic: hits agree, radiance agrees except on chaotic (deep specular) paths,
+    and the MEAN agrees within Monte-Carlo error (no bias)."""
+    rng = np.random.default_rng(11)
+    W, H, n = 320, 180, 200000
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, n)
+    ohit, orad, oray, _ = oracle_port.samples(sph, cam, W, H, 2, 3, xs, ys, sx, sy, ss)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        hit, rad, ray, _ = r.trace_samples(3, xs, ys, sx, sy, ss, gpu.PRECISION_FP32)
+    assert (hit == ohit).mean() >= 0.9999
+    assert np.abs(ray - oray).max() < 1e-5
+    rel = rel_err(rad, orad)
+    assert (rel <= 1e-3).mean() >= 0.985
+    se = np.sqrt((rad.var(axis=0) + orad.var(axis=0)) / n)
+    z = (rad.mean(axis=0) - orad.mean(axis=0)) / se
+    assert np.abs(z).max() < 4.0, f"FP32 mean radiance biased: z = {z}"
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fp32_image_against_oracle_same_seed(gpu, oracle_port, name):
+    W, H, S = 160, 90, 8
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    ref = oracle_port.render(sph, cam, W, H, S, 2, 17, 0)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(17, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL)
+        img = r.resolve()
+        st = r.stats()
+        acc = r.download_accum()
+    assert np.all(acc[:, 3] == S), "every sub-pixel must receive exactly S samples"
+    assert np.abs(img - ref).mean() < 2e-3
+    assert (np.abs(img - ref) < 1e-4).mean() > 0.95
+    assert abs(st.rays / st.paths - {"simple": 2.09, "box": 12.33, "box_mirror": 12.33, "dof_glass": 2.1}[name]) < 0.25
+
+
+def test_fp32_image_rmse_within_monte_carlo_noise(gpu, oracle_port):
+    """Independent seeds: RMSE(GPU, reference mean) within the Monte-Carlo bound estimated from K reference renders
+    ('Image RMSE')."""
+    W, H, S, K = 96, 72, 8, 6
+    sph, cfg = gpu.builtin_scene("box", W, H)
+    cam = gpu.camera_with_config(cfg)
+    refs = np.stack([oracle_port.render(sph, cam, W, H, S, 2, 1000 + k, 0) for k in range(K)])
+    mean_ref, var_px = refs.mean(axis=0), refs.var(axis=0, ddof=1)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(4242, 0, S, gpu.PRECISION_FP32)
+        img = r.resolve()
+    for c in range(3):
+        rmse = np.sqrt(np.mean((img[..., c] - mean_ref[..., c]) ** 2))
+        bound = 1.25 * np.sqrt(np.mean(var_px[..., c]) * (1.0 / K + 1.0))
+        assert rmse <= bound, f"channel {c}: RMSE {rmse:.4g} > noise bound {bound:.4g}"
+
+
+# ---- semantics that must survive the boundary ------------------------------------------------------
+def test_progressive_accumulation_and_sample_split(gpu):
+    """render(0,8) == render(0,3) + render(3,5): what lets ranks split the samples of a sub-pixel."""
+    W, H = 64, 40
+    sph, cfg = gpu.builtin_scene("box_mirror", W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(5, 0, 8, gpu.PRECISION_FP64)
+        a = r.resolve()
+        r.clear()
+        r.render(5, 0, 3, gpu.PRECISION_FP64)
+        r.render(5, 3, 5, gpu.PRECISION_FP64)
+        b = r.resolve()
+        assert np.abs(a - b).max() < 1e-12
+        r.clear()
+        r.render(5, 0, 8, gpu.PRECISION_FP32)
+        c = r.download_accum()
+        r.clear()
+        r.render(5, 3, 5, gpu.PRECISION_FP32)
+        r.render(5, 0, 3, gpu.PRECISION_FP32)
+        d = r.download_accum()
+    assert np.all(c[:, 3] == 8) and np.all(d[:, 3] == 8)
+    assert np.allclose(c[:, :3], d[:, :3], rtol=1e-5, atol=1e-5)  # same samples, different summation order
+
+
+def test_resolve_clamps_per_subpixel_and_flips_rows(gpu):
+    """main.cpp:181,195-196: mean -> clamp EACH stratum -> average; output row H-1-y."""
+    W, H = 32, 20
+    sph, cfg = gpu.builtin_scene("simple", W, H)  # directly visible E=30 light: strata means far above 1
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(2, 0, 16, gpu.PRECISION_FP32)
+        acc = r.download_accum().astype(np.float64)
+        img = r.resolve()
+        rgb8 = r.resolve_rgb8()
+    mean = acc[:, :3] / acc[:, 3:4]
+    assert mean.max() > 1.5, "test needs over-bright strata"
+    expect = np.clip(mean, 0.0, 1.0).reshape(H, W, 4, 3)
+    expect = ((expect[:, :, 0] * 0.25 + expect[:, :, 1] * 0.25) + expect[:, :, 2] * 0.25) + expect[:, :, 3] * 0.25
+    assert np.abs(img - expect[::-1]).max() < 1e-12
+    wrong = np.clip(mean.reshape(H, W, 4, 3).mean(axis=2), 0, 1)[::-1]  # clamping the pixel instead
+    assert np.abs(img - wrong).max() > 0.05
+    assert np.array_equal(rgb8.astype(np.int32), np.round(np.clip(img, 0, 1) ** (1 / 2.2) * 255).astype(np.int32))
+
+
+def test_spp_below_four_is_black_like_the_reference(gpu):
+    img = gpu.render_scene("box", 16, 12, 3)  # main.cpp:206: 3 / 4 == 0 samples
+    assert np.all(img == 0.0)
+
+
+def test_edge_geometries(gpu, oracle_port):
+    for (W, H) in ((1, 1), (3, 1), (7, 5), (33, 2)):  # far fewer / not a multiple of 32 sub-pixels
+        sph, cfg = gpu.builtin_scene("box", W, H)
+        cam = gpu.camera_with_config(cfg)
+        ref = oracle_port.render(sph, cam, W, H, 5, 2, 31, 0)
+        with make_renderer(gpu, sph, cam, W, H) as r:
+            r.render(31, 0, 5, gpu.PRECISION_FP32)
+            acc = r.download_accum()
+            img = r.resolve()
+        assert np.all(acc[:, 3] == 5)
+        assert np.abs(img - ref).mean() < 2e-2
+
+
+def test_single_sphere_and_strided_records(gpu, oracle_port):
+    W, H = 48, 32
+    one = np.zeros(1, dtype=gpu.SPHERE_DTYPE)
+    one["radius"], one["position"], one["color"], one["emission"] = 0.5, (0, 0, -1), (0.5, 0.6, 0.7), (0.2, 0.1, 0.0)
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    ref = oracle_port.render(one, cam, W, H, 4, 2, 1, 0)
+    padded = np.zeros((1, 128), dtype=np.uint8)  # a caller whose sphere struct is bigger than 88 bytes
+    padded[0, :88] = one.view(np.uint8)
+    with gpu.Renderer(0) as r:
+        r.upload_scene(padded.reshape(-1), stride=128)
+        r.set_camera(cam)
+        r.set_image(W, H, 2)
+        r.render(1, 0, 4, gpu.PRECISION_FP64)
+        img = r.resolve()
+    assert np.abs(img - ref).max() < 1e-9
+
+
+def test_generic_kernel_for_unspecialised_scene(gpu, oracle_port):
+    """A sphere count with no unrolled specialisation goes through the run-time-count kernel."""
+    rng = np.random.default_rng(4)
+    n = 23
+    s = np.zeros(n, dtype=gpu.SPHERE_DTYPE)
+    s["radius"] = rng.uniform(0.05, 0.3, n)
+    s["position"] = rng.uniform(-1, 1, (n, 3)) + (0, 0, -1)
+    s["color"] = rng.uniform(0.2, 0.9, (n, 3))
+    s["emission"][::5] = (2, 2, 2)
+    s["reflection"] = rng.integers(0, 3, n)
+    s[0] = (1000.0, (0, -1001.2, -1), (0, 0, 0), (0.5, 0.5, 0.5), 0, 0)
+    W, H, S = 80, 60, 6
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    ref = oracle_port.render(s, cam, W, H, S, 2, 9, 0)
+    with make_renderer(gpu, s, cam, W, H) as r:
+        r.render(9, 0, S, gpu.PRECISION_FP32)
+        img = r.resolve()
+        r.clear()
+        r.render(9, 0, S, gpu.PRECISION_FP64)
+        img64 = r.resolve()
+    assert (np.abs(img64 - ref) <= 1e-9).mean() >= 0.995
+    assert np.abs(img - ref).mean() < 4e-3
+
+
+def test_error_behaviour(gpu):
+    with gpu.Renderer(0) as r:
+        with pytest.raises(gpu.PtbError) as e:
+            r.render(1, 0, 1)
+        assert e.value.code == -4  # PTB_ERR_STATE: no scene yet
+        sph, cfg = gpu.builtin_scene("box", 8, 8)
+        bad = sph.copy()
+        bad["reflection"][3] = 7
+        with pytest.raises(gpu.PtbError) as e:
+            r.upload_scene(bad)
+        assert e.value.code == -1
+        r.upload_scene(sph)
+        with pytest.raises(gpu.PtbError) as e:
+            r.set_camera(np.zeros(10))
+        assert e.value.code == -1
+        r.set_camera(gpu.camera_with_config(cfg))
+        with pytest.raises(gpu.PtbError) as e:
+            r.render(1, 0, 1)  # no image yet
+        assert e.value.code == -4
+        with pytest.raises(gpu.PtbError):
+            r.set_image(0, 8, 2)
+        r.set_image(8, 8, 2)
+        with pytest.raises(gpu.PtbError) as e:
+            r.render(1, 0, 1, 0x100)  # unknown flag
+        assert e.value.code == -1
+        with pytest.raises(gpu.PtbError):
+            r.render(1, 0xFFFFFFFF, 2)  # sample range overflow
+        with pytest.raises(gpu.PtbError):
+            r.trace_samples(1, [8], [0], [0], [0], [0])  # x outside the image
+        r.render(1, 0, 1)
+        assert r.stats().paths == 8 * 8 * 4
+    with pytest.raises(gpu.PtbError) as e:
+        gpu.Renderer(10_000)
+    assert e.value.code == -2
+
+
+# ---- BASELINE.json full sizes through size-independent properties -------------------------------------------------------------------
+@pytest.mark.parametrize("cfg_name,scene,W,H", [("C2", "box", 1024, 768), ("C3", "box_mirror", 1920, 1080),
+                                                ("C4", "dof_glass", 3840, 2160)])
+def test_full_size_frames(gpu, cfg_name, scene, W, H):
+    S = 2
+    sph, cfg = gpu.builtin_scene(scene, W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(1, 0, S)
+        r.render(1, S, S)  # progressive second pass
+        acc = r.download_accum()
+        st = r.stats()
+        img = r.resolve()
+    assert acc.shape[0] == W * H * 4
+    assert np.all(acc[:, 3] == 2 * S), "sample count per sub-pixel"
+    assert st.paths == W * H * 4 * 2 * S
+    assert np.isfinite(acc).all() and acc[:, :3].min() >= 0.0
+    assert img.shape == (H, W, 3) and img.min() >= 0.0 and img.max() <= 1.0
+    expect_rpp = {"box": 12.33, "box_mirror": 12.33, "dof_glass": 2.05}[scene]
+    assert abs(st.rays / st.paths - expect_rpp) < 0.05 * expect_rpp + 0.05
+    # checksum of checksums: total radiance == sum over per-row sums, and the two halves of the frame are
+    # statistically alike for the left/right-symmetric box scenes
+    total = acc[:, :3].astype(np.float64).sum()
+    rows = acc[:, :3].astype(np.float64).reshape(H, -1).sum(axis=1)
+    assert abs(total - rows.sum()) <= 1e-9 * abs(total)
+
+
+def test_spheres10k_small_frame(gpu, oracle_port):
+    """BASELINE config 5 geometry (10 001 spheres) on a small frame: the run-time-count kernel with geometry
+    streamed from global memory."""
+    W, H, S = 64, 36, 2
+    sph, cfg = gpu.builtin_scene("spheres10k", W, H)
+    cam = gpu.camera_with_config(cfg)
+    rng = np.random.default_rng(2)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, 3000)
+    ohit, orad, _, _ = oracle_port.samples(sph, cam, W, H, 2, 6, xs, ys, sx, sy, ss)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        hit, rad, _, _ = r.trace_samples(6, xs, ys, sx, sy, ss, gpu.PRECISION_FP64)
+        assert np.array_equal(hit, ohit)
+        assert (rel_err(rad, orad) <= REL_TOL).mean() >= 0.995
+        hit32, rad32, _, _ = r.trace_samples(6, xs, ys, sx, sy, ss, gpu.PRECISION_FP32)
+        assert (hit32 == ohit).mean() >= 0.999
+        r.render(6, 0, S)
+        acc = r.download_accum()
+    assert np.all(acc[:, 3] == S)
