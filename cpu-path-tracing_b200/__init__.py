@@ -89,6 +89,7 @@ _ptb_last_error = _sig("ptb_last_error", ctypes.c_char_p, _vp)
 _ptb_create = _sig("ptb_create", ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp))
 _ptb_destroy = _sig("ptb_destroy", None, _vp)
 _ptb_set_stream = _sig("ptb_set_stream", ctypes.c_int, _vp, _vp)
+_ptb_reset_stream = _sig("ptb_reset_stream", ctypes.c_int, _vp)
 _ptb_synchronize = _sig("ptb_synchronize", ctypes.c_int, _vp)
 _ptb_upload_scene = _sig("ptb_upload_scene", ctypes.c_int, _vp, _vp, _sz, _sz)
 _ptb_set_camera = _sig("ptb_set_camera", ctypes.c_int, _vp, _vp, _sz)
@@ -114,7 +115,7 @@ _ptb_write_ppm = _sig("ptb_write_ppm", ctypes.c_int, ctypes.c_char_p, _vp, ctype
 # every symbol include/ptb200.h declares (tests check the header against this list and the .so)
 EXPORTED_SYMBOLS = (
     "ptb_abi_version", "ptb_device_count", "ptb_last_error", "ptb_create", "ptb_destroy", "ptb_set_stream",
-    "ptb_synchronize", "ptb_upload_scene", "ptb_set_camera", "ptb_set_image", "ptb_clear", "ptb_render",
+    "ptb_reset_stream", "ptb_synchronize", "ptb_upload_scene", "ptb_set_camera", "ptb_set_image", "ptb_clear", "ptb_render",
     "ptb_resolve", "ptb_resolve_rgb8", "ptb_resolve_device", "ptb_measure_fp32_peak", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
     "ptb_get_stats", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
     "ptb_write_ppm",
@@ -241,8 +242,12 @@ class Renderer:
         self._check(_ptb_set_image(self._ctx, width, height, num_subpixels))
         self.width, self.height, self.nsub = width, height, num_subpixels
 
-    def set_stream(self, cuda_stream: int | None):
+    def set_stream(self, cuda_stream: int):
+        """Run on this cudaStream_t handle; 0 is the legacy default stream (torch's default current stream)."""
         self._check(_ptb_set_stream(self._ctx, _vp(cuda_stream) if cuda_stream else None))
+
+    def reset_stream(self):
+        self._check(_ptb_reset_stream(self._ctx))
 
     def synchronize(self):
         self._check(_ptb_synchronize(self._ctx))

@@ -430,7 +430,18 @@ int ptb_set_stream(ptb_context* ctx, void* cuda_stream)
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream); // nullptr == the legacy default stream
+    return PTB_OK;
+}
+
+int ptb_reset_stream(ptb_context* ctx)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return PTB_OK;
 }
 

@@ -87,9 +87,12 @@ char const* ptb_last_error(ptb_context const* ctx);
 /* Replaces tf::Executor / tf::Taskflow construction, src/main.cpp:214-215. */
 int ptb_create(int device, ptb_context** out);
 void ptb_destroy(ptb_context* ctx);
-/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the
- * stream a framework is recording events on.  NULL = the context's own stream. */
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the stream a
+ * framework is recording events on.  NULL is the CUDA legacy default stream (handle 0),
+ * which is what torch.cuda.current_stream().cuda_stream is unless a side stream is set.
+ * A fresh context runs on a private non-blocking stream; ptb_reset_stream returns to it. */
 int ptb_set_stream(ptb_context* ctx, void* cuda_stream);
+int ptb_reset_stream(ptb_context* ctx);
 int ptb_synchronize(ptb_context* ctx);
 
 /* ---- inputs ------------------------------------------------------------------ */

