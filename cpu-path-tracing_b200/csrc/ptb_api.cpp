@@ -36,11 +36,10 @@ struct ptb_context
     RawCamera* d_camera = nullptr;
     ConstSceneF32 cs{};
     double shift[3] = { 0, 0, 0 };
-    int n_small = 0, n_big = 0;
+    SceneCounts counts{ 0, 0, 0, 0, true };
     SmallGeo* d_small = nullptr;
     BigGeo* d_big = nullptr;
-    int* d_small_id = nullptr;
-    int* d_big_id = nullptr;
+    int* d_order = nullptr;
     float4* d_shade = nullptr; // 4 planes of n
     size_t geo_cap = 0;
 
@@ -129,11 +128,26 @@ void pack_scene(ptb_context* ctx)
 
 struct PackedScene
 {
-    std::vector<SmallGeo> small_geo;
-    std::vector<BigGeo> big_geo;
-    std::vector<int> small_id, big_id;
-    std::vector<float4> shade; // 4 planes
+    std::vector<SmallGeo> small_geo; // near-only first, then both-roots
+    std::vector<BigGeo> big_geo;     // near-only first, then both-roots
+    std::vector<int> order;          // list position -> original index
+    std::vector<float4> shade;       // 4 planes, by list position
+    SceneCounts counts{ 0, 0, 0, 0, true };
 };
+
+// A sphere can only ever be hit at its NEAR root when no ray origin can lie inside it:
+// it must be opaque (diffuse / specular scatter back to the outside, main.cpp:44-67) and the
+// camera lens (position +- the largest lens offset, camera.cpp:34-35: |rd*(s+t)| <= 2*sqrt(2)*lens_radius)
+// must be outside it.  Dielectric spheres are traversed from inside and keep both roots.
+bool near_root_only(RawSphere const& s, RawCamera const& cam, bool have_camera)
+{
+    if(s.reflection == 2 || !have_camera) {
+        return false;
+    }
+    double const dx = cam.pos[0] - s.px, dy = cam.pos[1] - s.py, dz = cam.pos[2] - s.pz;
+    double const dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+    return dist > s.radius + 3.0 * std::fabs(cam.lens_radius) + 1e-9;
+}
 
 PackedScene pack_geometry(ptb_context* ctx)
 {
@@ -141,8 +155,28 @@ PackedScene pack_geometry(ptb_context* ctx)
     std::vector<RawSphere> const& s = ctx->h_spheres;
     double const* sh = ctx->shift;
     PackedScene out;
-    out.shade.resize(static_cast<size_t>(4) * static_cast<size_t>(std::max(n, 1)));
+
+    // list order: [small near-only, small both, big near-only, big both], original order inside each
+    std::vector<int> lists[4];
     for(int i = 0; i < n; ++i) {
+        bool const big = s[i].radius > kBigRadius;
+        bool const near_only = near_root_only(s[i], ctx->h_camera, ctx->have_camera);
+        lists[(big ? 2 : 0) + (near_only ? 0 : 1)].push_back(i);
+    }
+    out.counts.small_near = static_cast<int>(lists[0].size());
+    out.counts.small_both = static_cast<int>(lists[1].size());
+    out.counts.big_near = static_cast<int>(lists[2].size());
+    out.counts.big_both = static_cast<int>(lists[3].size());
+    out.counts.fits_const = out.counts.small_near + out.counts.small_both <= kMaxConstSpheres &&
+                            out.counts.big_near + out.counts.big_both <= kMaxConstSpheres;
+    for(auto const& l : lists) {
+        out.order.insert(out.order.end(), l.begin(), l.end());
+    }
+
+    size_t const N = static_cast<size_t>(std::max(n, 1));
+    out.shade.resize(4 * N);
+    for(int pos = 0; pos < n; ++pos) {
+        int const i = out.order[static_cast<size_t>(pos)];
         double const R = s[i].radius;
         double const x = s[i].px - sh[0], y = s[i].py - sh[1], z = s[i].pz - sh[2];
         if(R > kBigRadius) {
@@ -155,7 +189,6 @@ PackedScene pack_geometry(ptb_context* ctx)
             b.K = static_cast<float>(k * ((x * x + y * y + z * z) - R * R));
             b.two_r = static_cast<float>(2.0 * R);
             out.big_geo.push_back(b);
-            out.big_id.push_back(i);
         }
         else {
             SmallGeo g{};
@@ -164,7 +197,6 @@ PackedScene pack_geometry(ptb_context* ctx)
             g.cz = static_cast<float>(z);
             g.r2 = static_cast<float>(R * R);
             out.small_geo.push_back(g);
-            out.small_id.push_back(i);
         }
         double const inv_r = R != 0.0 ? 1.0 / R : 0.0;
         double const p = std::max({ s[i].cr, s[i].cg, s[i].cb });
@@ -187,11 +219,11 @@ PackedScene pack_geometry(ptb_context* ctx)
         d.y = static_cast<float>(s[i].cg * inv_p);
         d.z = static_cast<float>(s[i].cb * inv_p);
         d.w = 0.0f;
-        size_t const N = static_cast<size_t>(n);
-        out.shade[i] = a;
-        out.shade[N + i] = b;
-        out.shade[2 * N + i] = c;
-        out.shade[3 * N + i] = d;
+        size_t const P = static_cast<size_t>(pos);
+        out.shade[P] = a;
+        out.shade[N + P] = b;
+        out.shade[2 * N + P] = c;
+        out.shade[3 * N + P] = d;
     }
     return out;
 }
@@ -227,54 +259,54 @@ int rebuild_device_scene(ptb_context* ctx)
     PackedScene const ps = pack_geometry(ctx);
     pack_camera(ctx);
     int const n = ctx->n;
-    ctx->n_small = static_cast<int>(ps.small_geo.size());
-    ctx->n_big = static_cast<int>(ps.big_geo.size());
-    ctx->cs.n_small = ctx->n_small;
-    ctx->cs.n_big = ctx->n_big;
+    ctx->counts = ps.counts;
+    int const n_small = ps.counts.small_near + ps.counts.small_both;
+    int const n_big = ps.counts.big_near + ps.counts.big_both;
+    ctx->cs.n_small_near = ps.counts.small_near;
+    ctx->cs.n_small = n_small;
+    ctx->cs.n_big_near = ps.counts.big_near;
+    ctx->cs.n_big = n_big;
     ctx->cs.n_total = n;
-    for(int i = 0; i < std::min(ctx->n_small, kMaxConstSpheres); ++i) {
-        ctx->cs.small_geo[i] = ps.small_geo[static_cast<size_t>(i)];
-        ctx->cs.small_id[i] = ps.small_id[static_cast<size_t>(i)];
-    }
-    for(int i = 0; i < std::min(ctx->n_big, kMaxConstSpheres); ++i) {
-        ctx->cs.big_geo[i] = ps.big_geo[static_cast<size_t>(i)];
-        ctx->cs.big_id[i] = ps.big_id[static_cast<size_t>(i)];
+    if(ps.counts.fits_const) {
+        for(int i = 0; i < n_small; ++i) {
+            ctx->cs.small_geo[i] = ps.small_geo[static_cast<size_t>(i)];
+        }
+        for(int i = 0; i < n_big; ++i) {
+            ctx->cs.big_geo[i] = ps.big_geo[static_cast<size_t>(i)];
+        }
+        for(int i = 0; i < n; ++i) {
+            ctx->cs.order[i] = ps.order[static_cast<size_t>(i)];
+        }
     }
 
     size_t const cap = static_cast<size_t>(std::max(n, 1));
     if(cap > ctx->geo_cap) {
         cudaFree(ctx->d_small);
         cudaFree(ctx->d_big);
-        cudaFree(ctx->d_small_id);
-        cudaFree(ctx->d_big_id);
+        cudaFree(ctx->d_order);
         cudaFree(ctx->d_shade);
         ctx->d_small = nullptr;
         ctx->d_big = nullptr;
-        ctx->d_small_id = nullptr;
-        ctx->d_big_id = nullptr;
+        ctx->d_order = nullptr;
         ctx->d_shade = nullptr;
         ctx->geo_cap = 0;
         PTB_CUDA(ctx, cudaMalloc(&ctx->d_small, cap * sizeof(SmallGeo)));
         PTB_CUDA(ctx, cudaMalloc(&ctx->d_big, cap * sizeof(BigGeo)));
-        PTB_CUDA(ctx, cudaMalloc(&ctx->d_small_id, cap * sizeof(int)));
-        PTB_CUDA(ctx, cudaMalloc(&ctx->d_big_id, cap * sizeof(int)));
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_order, cap * sizeof(int)));
         PTB_CUDA(ctx, cudaMalloc(&ctx->d_shade, 4 * cap * sizeof(float4)));
         ctx->geo_cap = cap;
     }
     cudaStream_t const st = ctx->stream;
-    if(ctx->n_small > 0) {
+    if(n_small > 0) {
         PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ps.small_geo.data(), ps.small_geo.size() * sizeof(SmallGeo),
                                       cudaMemcpyHostToDevice, st));
-        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_small_id, ps.small_id.data(), ps.small_id.size() * sizeof(int),
-                                      cudaMemcpyHostToDevice, st));
     }
-    if(ctx->n_big > 0) {
+    if(n_big > 0) {
         PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_big, ps.big_geo.data(), ps.big_geo.size() * sizeof(BigGeo),
-                                      cudaMemcpyHostToDevice, st));
-        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_id, ps.big_id.data(), ps.big_id.size() * sizeof(int),
                                       cudaMemcpyHostToDevice, st));
     }
     if(n > 0) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ps.order.data(), ps.order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_shade, ps.shade.data(), 4 * static_cast<size_t>(n) * sizeof(float4),
                                       cudaMemcpyHostToDevice, st));
     }
@@ -298,8 +330,7 @@ GeoLists geo_lists(ptb_context* ctx)
     GeoLists g;
     g.small_geo = ctx->d_small;
     g.big_geo = ctx->d_big;
-    g.small_id = ctx->d_small_id;
-    g.big_id = ctx->d_big_id;
+    g.order = ctx->d_order;
     return g;
 }
 
@@ -403,8 +434,7 @@ void ptb_destroy(ptb_context* ctx)
     cudaFree(ctx->d_camera);
     cudaFree(ctx->d_small);
     cudaFree(ctx->d_big);
-    cudaFree(ctx->d_small_id);
-    cudaFree(ctx->d_big_id);
+    cudaFree(ctx->d_order);
     cudaFree(ctx->d_shade);
     cudaFree(ctx->d_accum);
     cudaFree(ctx->d_accum64);
@@ -640,8 +670,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         p.shade = shade_planes(ctx);
         p.geo = geo_lists(ctx);
         p.n_total = ctx->n;
-        int const ns_spec = ctx->n_small <= kMaxConstSpheres && ctx->n_big <= kMaxConstSpheres ? ctx->n_small : -1;
-        PTB_CUDA(ctx, launch_megakernel(p, ns_spec, ctx->n_big, ctx->sm_count, st, &launches));
+        PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches));
     }
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     PTB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -898,8 +927,7 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
     }
     else {
         PTB_CUDA_T(upload_const_scene(ctx->cs, st));
-        int const ns_spec = ctx->n_small <= kMaxConstSpheres && ctx->n_big <= kMaxConstSpheres ? ctx->n_small : -1;
-        PTB_CUDA_T(launch_probe_f32(q, ns_spec, ctx->n_big, shade_planes(ctx), geo_lists(ctx), st));
+        PTB_CUDA_T(launch_probe_f32(q, ctx->counts, shade_planes(ctx), geo_lists(ctx), st));
     }
     ctx->stats.kernel_launches += 1;
     PTB_CUDA_T(cudaMemcpyAsync(primary_hit_out, d_hit, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

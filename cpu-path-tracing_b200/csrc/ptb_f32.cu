@@ -57,12 +57,13 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
 constexpr int kRingSize = 64; // entries per warp, power of two, >= 2 * 32
 struct WarpRing
 {
-    float4 a[kRingSize]; // ox, oy, dx, dy
-    float4 b[kRingSize]; // dz, rng.state, rng.inc, slot (bits); oz is the camera's z (lens offset has no z)
+    float4 a[kRingSize];      // ox, oy, dx, dy        (oz is the camera's z: the lens offset has no z)
+    float4 b[kRingSize];      // dz, len, rng.state, rng.inc
+    uint32_t slot[kRingSize]; // sub-pixel slot, kVoidSlot = nothing to trace
 };
 constexpr uint32_t kVoidSlot = 0xFFFFFFFFu;
 
-template<int NS, int NB, bool kSmemShade>
+template<class Shape, bool kSmemShade>
 __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 const prm)
 {
     __shared__ float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
             }
             if(!exhausted) {
                 PathF32 g;
-                g.dx = g.dy = g.dz = g.ox = g.oy = 0.0f;
+                g.dx = g.dy = g.dz = g.ox = g.oy = g.len = 0.0f;
                 g.rng.state = g.rng.inc = 0u;
                 if(gen_slot != kVoidSlot) {
                     g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                 }
                 uint32_t const w = (ring_head + lane) & (kRingSize - 1);
                 ring.a[w] = make_float4(g.ox, g.oy, g.dx, g.dy);
-                ring.b[w] = make_float4(g.dz, __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc),
-                                        __uint_as_float(gen_slot));
+                ring.b[w] = make_float4(g.dz, g.len, __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc));
+                ring.slot[w] = gen_slot;
                 ring_head = (ring_head + 32u) & (kRingSize - 1);
                 ring_count += 32u;
                 next_sample += 1u;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                 uint32_t const rd = (ring_tail + rank) & (kRingSize - 1);
                 float4 const ea = ring.a[rd];
                 float4 const eb = ring.b[rd];
-                slot = __float_as_uint(eb.w);
+                slot = ring.slot[rd];
                 if(slot != kVoidSlot) {
                     p.ox = ea.x;
                     p.oy = ea.y;
@@ -161,8 +162,9 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                     p.dx = ea.z;
                     p.dy = ea.w;
                     p.dz = eb.x;
-                    p.rng.state = __float_as_uint(eb.y);
-                    p.rng.inc = __float_as_uint(eb.z);
+                    p.len = eb.y;
+                    p.rng.state = __float_as_uint(eb.z);
+                    p.rng.inc = __float_as_uint(eb.w);
                     p.tr = p.tg = p.tb = 1.0f;
                     p.er = p.eg = p.eb = 0.0f;
                     p.depth = 0;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
             RayTerms const r = ray_terms(p);
             float t;
             int id;
-            bool const hit = closest_hit<NS, NB>(c_scene, prm.geo, p, r, t, id);
+            bool const hit = closest_hit<Shape>(c_scene, prm.geo, p, r, t, id);
             cnt.rays++;
             alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
             if(!alive) {
@@ -209,20 +211,21 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
 }
 
 // ---- specialisation table ------------------------------------------------------------------
-// (n_small, n_big) pairs with a fully unrolled kernel.  Everything else runs the
-// generic run-time-count variant.
+// (small near-only, small both-roots, big near-only, big both-roots) list lengths with a fully
+// unrolled kernel.  Everything else runs the generic run-time-count variant.
 #define PTB_MEGA_SPECIALISATIONS(X) \
-    X(3, 5) /* box_scene.hpp / box_mirror_scene.hpp: 3 small spheres + 5 R=1e6 walls */ \
-    X(4, 1) /* simple_scene.hpp and the depth-of-field glass scene: 4 small + ground  */ \
-    X(5, 0) \
-    X(8, 0) \
-    X(1, 0) \
-    X(0, 1)
+    X(2, 1, 5, 0) /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball, glass ball, 5 R=1e6 walls */ \
+    X(3, 1, 1, 0) /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100)                    */ \
+    X(2, 2, 1, 0) /* depth-of-field scene (BASELINE config 4): two glass spheres                        */ \
+    X(0, 3, 0, 5) /* box scenes with the camera inside a sphere / all-both fallback                     */ \
+    X(1, 0, 0, 0) \
+    X(0, 1, 0, 0) \
+    X(8, 0, 0, 0)
 
-bool megakernel_has_specialisation(int n_small, int n_big)
+bool megakernel_has_specialisation(int sn, int sb, int bn, int bb)
 {
-#define X(a, b) \
-    if(n_small == (a) && n_big == (b)) { \
+#define X(a, b, c, d) \
+    if(sn == (a) && sb == (b) && bn == (c) && bb == (d)) { \
         return true; \
     }
     PTB_MEGA_SPECIALISATIONS(X)
@@ -230,31 +233,31 @@ bool megakernel_has_specialisation(int n_small, int n_big)
     return false;
 }
 
-template<int NS, int NB, bool kSmem>
+template<class Shape, bool kSmem>
 static cudaError_t launch_one(RenderParamsF32 const& p, int sm_count, cudaStream_t stream)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel<NS, NB, kSmem>, kMegaThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel<Shape, kSmem>, kMegaThreads, 0);
     if(e != cudaSuccess) {
         return e;
     }
     if(per_sm < 1) {
         per_sm = 1;
     }
-    unsigned long long const warps_needed = (static_cast<unsigned long long>(p.ntiles) + 0ull);
     unsigned long long blocks = static_cast<unsigned long long>(sm_count) * static_cast<unsigned long long>(per_sm);
-    unsigned long long const blocks_needed = (warps_needed + (kMegaThreads / 32) - 1) / (kMegaThreads / 32);
+    unsigned long long const blocks_needed =
+        (static_cast<unsigned long long>(p.ntiles) + (kMegaThreads / 32) - 1) / (kMegaThreads / 32);
     if(blocks > blocks_needed) {
         blocks = blocks_needed;
     }
     if(blocks < 1) {
         blocks = 1;
     }
-    mega_kernel<NS, NB, kSmem><<<static_cast<unsigned>(blocks), kMegaThreads, 0, stream>>>(p);
+    mega_kernel<Shape, kSmem><<<static_cast<unsigned>(blocks), kMegaThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_megakernel(RenderParamsF32 const& p, int n_small, int n_big, int sm_count, cudaStream_t stream,
+cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
                               int* launches)
 {
     cudaError_t e = cudaMemsetAsync(&p.counters->tile_cursor, 0, sizeof(unsigned long long), stream);
@@ -265,22 +268,22 @@ cudaError_t launch_megakernel(RenderParamsF32 const& p, int n_small, int n_big, 
         *launches += 1;
     }
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b) \
-    if(n_small == (a) && n_big == (b) && smem) { \
-        return launch_one<(a), (b), true>(p, sm_count, stream); \
+#define X(a, b, cc, d) \
+    if(c.small_near == (a) && c.small_both == (b) && c.big_near == (cc) && c.big_both == (d) && smem && c.fits_const) { \
+        return launch_one<SceneShape<(a), (b), (cc), (d)>, true>(p, sm_count, stream); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X
     if(smem) {
-        return launch_one<-1, -1, true>(p, sm_count, stream);
+        return launch_one<GenericShape, true>(p, sm_count, stream);
     }
-    return launch_one<-1, -1, false>(p, sm_count, stream);
+    return launch_one<GenericShape, false>(p, sm_count, stream);
 }
 
 // ---- FP32 probe ---------------------------------------------------------------------------------
 // One thread per requested sample; same device functions AND the same (n_small, n_big)
 // specialisation as the megakernel, so the probe traces what the renderer traces.
-template<int NS, int NB>
+template<class Shape>
 __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoLists const geo)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,11 +300,17 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         q.ray[6 * i + 0] = p.ox;
         q.ray[6 * i + 1] = p.oy;
         q.ray[6 * i + 2] = p.oz;
-        q.ray[6 * i + 3] = p.dx;
-        q.ray[6 * i + 4] = p.dy;
-        q.ray[6 * i + 5] = p.dz;
+        q.ray[6 * i + 3] = p.dx * p.len; // report the reference's un-normalised direction
+        q.ray[6 * i + 4] = p.dy * p.len;
+        q.ray[6 * i + 5] = p.dz * p.len;
     }
-    q.primary_hit[i] = primary_hit_index<NS, NB>(c_scene, geo, p);
+    {
+        RayTerms const r0 = ray_terms(p);
+        float t0;
+        int pos;
+        bool const hit0 = closest_hit<Shape>(c_scene, geo, p, r0, t0, pos);
+        q.primary_hit[i] = hit0 ? geo.order[pos] : -1; // list position -> the caller's sphere index
+    }
 
     BounceCounters cnt{ 0, 0, 0, 0 };
     bool alive = true;
@@ -309,7 +318,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         RayTerms const r = ray_terms(p);
         float t;
         int id;
-        bool const hit = closest_hit<NS, NB>(c_scene, geo, p, r, t, id);
+        bool const hit = closest_hit<Shape>(c_scene, geo, p, r, t, id);
         alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
     }
     q.radiance[3 * i + 0] = p.er;
@@ -320,7 +329,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
     }
 }
 
-cudaError_t launch_probe_f32(ProbeParams const& p, int n_small, int n_big, ShadePlanes const& shade, GeoLists const& geo,
+cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade, GeoLists const& geo,
                              cudaStream_t stream)
 {
     if(p.count == 0) {
@@ -328,14 +337,14 @@ cudaError_t launch_probe_f32(ProbeParams const& p, int n_small, int n_big, Shade
     }
     unsigned const threads = 128;
     unsigned const blocks = (p.count + threads - 1) / threads;
-#define X(a, b) \
-    if(n_small == (a) && n_big == (b)) { \
-        probe_f32_kernel<(a), (b)><<<blocks, threads, 0, stream>>>(p, shade, geo); \
+#define X(a, b, cc, d) \
+    if(c.small_near == (a) && c.small_both == (b) && c.big_near == (cc) && c.big_both == (d) && c.fits_const) { \
+        probe_f32_kernel<SceneShape<(a), (b), (cc), (d)>><<<blocks, threads, 0, stream>>>(p, shade, geo); \
         return cudaGetLastError(); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X
-    probe_f32_kernel<-1, -1><<<blocks, threads, 0, stream>>>(p, shade, geo);
+    probe_f32_kernel<GenericShape><<<blocks, threads, 0, stream>>>(p, shade, geo);
     return cudaGetLastError();
 }
 

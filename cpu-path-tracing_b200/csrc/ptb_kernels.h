@@ -43,10 +43,16 @@ struct RenderParamsF32
 // Copy the packed scene into the constant bank the FP32 kernels read.
 cudaError_t upload_const_scene(ConstSceneF32 const& cs, cudaStream_t stream);
 
-// True when a kernel specialised for (n_small, n_big) exists.
-bool megakernel_has_specialisation(int n_small, int n_big);
-// Launch the persistent megakernel.  grid_blocks = 0 -> SM count * resident blocks.
-cudaError_t launch_megakernel(RenderParamsF32 const& p, int n_small, int n_big, int sm_count, cudaStream_t stream,
+// Lengths of the four geometry lists of a packed scene (ptb_scene.cuh)
+struct SceneCounts
+{
+    int small_near, small_both, big_near, big_both;
+    bool fits_const; // both classes fit the __constant__ lists
+};
+// True when a fully unrolled kernel exists for these list lengths.
+bool megakernel_has_specialisation(int small_near, int small_both, int big_near, int big_both);
+// Launch the persistent megakernel: grid = SM count * resident blocks.
+cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
                               int* launches);
 
 struct ProbeParams
@@ -64,7 +70,7 @@ struct ProbeParams
     double* ray;      // [count*6] or nullptr
     uint32_t* draws;  // [count] or nullptr
 };
-cudaError_t launch_probe_f32(ProbeParams const& p, int n_small, int n_big, ShadePlanes const& shade, GeoLists const& geo,
+cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade, GeoLists const& geo,
                              cudaStream_t stream);
 
 // ---- FP64 parity path (reference operation order, no FMA contraction) ----------------------------------

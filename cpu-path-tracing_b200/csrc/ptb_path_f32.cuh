@@ -59,7 +59,9 @@ __device__ __forceinline__ float fast_rsqrt(float x)
 struct PathF32
 {
     float ox, oy, oz; // ray origin (shifted frame)
-    float dx, dy, dz; // ray direction, NOT normalised (camera.cpp:36)
+    float dx, dy, dz; // ray direction, UNIT length (see `len`)
+    float len;        // length the reference's un-normalised direction would have (camera.cpp:36):
+                      // the reference compares roots in units of t_ref = t / len against epsilon
     float tr, tg, tb; // accumulated_reflectance (main.cpp:108)
     float er, eg, eb; // accumulated_emission   (main.cpp:107)
     Rng rng;
@@ -86,7 +88,12 @@ __device__ __forceinline__ void slot_coords(uint32_t slot, uint32_t width, uint3
     x = pix - y * width;
 }
 
-// main.cpp:186-190 + camera.cpp:19-38
+// main.cpp:186-190 + camera.cpp:19-38.  The reference keeps the camera ray un-normalised
+// (|d| ~ focus distance) and a mirror bounce preserves that length, so its epsilon test
+// (sphere.cpp:21, in units of t) scales with |d|.  Here the direction is normalised ONCE,
+// when the sample is generated, and the original length travels with the path as `len`:
+// t_ref < epsilon  <=>  t_unit < epsilon * len.  That removes a = d.d, 1/a and every
+// multiplication by a from the sphere tests.
 __device__ __forceinline__ void gen_primary(PathF32& p, CameraF32 const& cam, uint32_t x, uint32_t y, uint32_t sx,
                                             uint32_t sy)
 {
@@ -112,20 +119,24 @@ __device__ __forceinline__ void gen_primary(PathF32& p, CameraF32 const& cam, ui
     p.ox = cam.px + offx;
     p.oy = cam.py + offy;
     p.oz = cam.pz;
-    p.dx = fmaf(cam.bx, t, fmaf(cam.ax, s, cam.rx)) - offx;
-    p.dy = fmaf(cam.by, t, fmaf(cam.ay, s, cam.ry)) - offy;
-    p.dz = fmaf(cam.bz, t, fmaf(cam.az, s, cam.rz));
+    float const dx = fmaf(cam.bx, t, fmaf(cam.ax, s, cam.rx)) - offx;
+    float const dy = fmaf(cam.by, t, fmaf(cam.ay, s, cam.ry)) - offy;
+    float const dz = fmaf(cam.bz, t, fmaf(cam.az, s, cam.rz));
+    float const d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    float const inv = fast_rsqrt(d2);
+    p.dx = dx * inv;
+    p.dy = dy * inv;
+    p.dz = dz * inv;
+    p.len = d2 * inv;
     p.tr = p.tg = p.tb = 1.0f;
     p.er = p.eg = p.eb = 0.0f;
     p.depth = 0;
 }
 
-// Per-ray invariants of the sphere tests (sphere.cpp:9 `a`, plus the expanded terms
-// of the big-sphere form).
+// Per-ray invariants of the sphere tests.
 struct RayTerms
 {
-    float a;     // d.d
-    float eps_a; // epsilon * a : roots are compared in units of a*t
+    float eps;   // epsilon * len : roots are compared in units of t along the UNIT direction
     float od;    // o.d
     float oo;    // o.o
     float o2x, o2y, o2z; // 2*o
@@ -134,8 +145,7 @@ struct RayTerms
 __device__ __forceinline__ RayTerms ray_terms(PathF32 const& p)
 {
     RayTerms r;
-    r.a = fmaf(p.dx, p.dx, fmaf(p.dy, p.dy, p.dz * p.dz));
-    r.eps_a = kEpsilon * r.a;
+    r.eps = kEpsilon * p.len;
     r.od = fmaf(p.ox, p.dx, fmaf(p.oy, p.dy, p.oz * p.dz));
     r.oo = fmaf(p.ox, p.ox, fmaf(p.oy, p.oy, p.oz * p.oz));
     r.o2x = p.ox + p.ox;
@@ -144,103 +154,135 @@ __device__ __forceinline__ RayTerms ray_terms(PathF32 const& p)
     return r;
 }
 
-// Candidate key of one sphere: bits of (a*t - eps*a) for the smallest root with
-// t >= eps, or something >= 0x7F800000 when there is none.  Non-negative floats
-// order like unsigned integers; negative values (root < eps) and NaN
-// (discriminant < 0, sphere.cpp:14) order ABOVE +inf, so a single unsigned min
-// does "root < eps -> try the far root -> reject" (sphere.cpp:21-27).
+// Candidate key of one sphere: bits of (t - eps) for the smallest root with t >= eps, or
+// something >= 0x7F800000 when there is none.  Non-negative floats order like unsigned
+// integers; negative values (root < eps) and NaN (discriminant < 0, sphere.cpp:14) order
+// ABOVE +inf, so a single unsigned min does "root < eps -> try the far root -> reject"
+// (sphere.cpp:21-27).  kBoth = false keeps the near root only (opaque sphere seen from
+// outside: the far root can never be the answer).
+template<bool kBoth>
 __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& p, RayTerms const& r)
 {
     float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz; // c - o = -oc
     float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));       // -half_b
     float const cc = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, -s.r2))); // c (sphere.cpp:11)
-    float const disc = fmaf(nb, nb, -(r.a * cc));
+    float const disc = fmaf(nb, nb, -cc);
     float const sq = disc_sqrt(disc);
-    float const h = nb - r.eps_a;
+    float const h = nb - r.eps;
     float const tn = h - sq;
-    float const tf = h + sq;
-    return min(__float_as_uint(tn), __float_as_uint(tf));
+    if constexpr(kBoth) {
+        float const tf = h + sq;
+        return min(__float_as_uint(tn), __float_as_uint(tf));
+    }
+    else {
+        return __float_as_uint(tn);
+    }
 }
 
+// Big-sphere form.  With m = sqrt(disc) + |hb| (no cancellation, m > 0) the two roots are
+//   sigma * c / m   and   sigma * m / k,     sigma = -sign(hb)  (+1 when approaching),
+// which is the numerically stable pairing for EITHER sign of hb: the earlier c/(sqrt - hb)
+// is only safe for hb <= 0; moving away from a sphere (hb > 0) it divides by a difference
+// that rounding can turn into a tiny POSITIVE number, i.e. a spurious hit ~1e7 away.
+template<bool kBoth>
 __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, RayTerms const& r)
 {
     float const hb = fmaf(p.dx, b.gx, fmaf(p.dy, b.gy, fmaf(p.dz, b.gz, b.k * r.od)));           // half_b / 2R
     float const cp = fmaf(r.o2x, b.gx, fmaf(r.o2y, b.gy, fmaf(r.o2z, b.gz, fmaf(b.k, r.oo, b.K)))); // c / 2R
-    float const ac = r.a * cp;
-    float const disc = fmaf(hb, hb, -(b.k * ac));
-    float const sq = disc_sqrt(disc);
-    float const den = sq - hb;
-    float const tn = fmaf(ac, fast_rcp(den), -r.eps_a); // a*c/(sqrt - hb): no cancellation for the near root
-    float const tf = fmaf(den, b.two_r, -r.eps_a);      // a*(sqrt - hb)/(a k)
-    return min(__float_as_uint(tn), __float_as_uint(tf));
+    float const disc = fmaf(hb, hb, -(b.k * cp));
+    float const m = disc_sqrt(disc) + fabsf(hb);
+    uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u; // sign bit set when hb >= 0 (sigma = -1)
+    float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
+    float const t1 = fmaf(cs, fast_rcp(m), -r.eps);
+    if constexpr(kBoth) {
+        float const ms = __uint_as_float(__float_as_uint(m) ^ flip);
+        float const t2 = fmaf(ms, b.two_r, -r.eps);
+        return min(__float_as_uint(t1), __float_as_uint(t2));
+    }
+    else {
+        return __float_as_uint(t1);
+    }
 }
 
-// main.cpp:30-42.  NS/NB >= 0: counts known at compile time, geometry read straight
-// from constant-bank operands, fully unrolled.  NS = NB = -1: run-time counts,
-// geometry from global memory (any scene size).
-template<int NS, int NB>
+// Compile-time description of a scene's four geometry lists; all -1 = run-time counts.
+template<int SN, int SB, int BN, int BB>
+struct SceneShape
+{
+    static constexpr int small_near = SN, small_both = SB, big_near = BN, big_both = BB;
+    static constexpr bool generic = SN < 0;
+    static constexpr int total = SN + SB + BN + BB;
+};
+using GenericShape = SceneShape<-1, -1, -1, -1>;
+
+// main.cpp:30-42.  Returns the LIST POSITION of the closest sphere (see ptb_scene.cuh).
+//  - specialised shapes: counts known at compile time, geometry read from constant-bank
+//    operands, fully unrolled; the list position rides in the low kIdBits mantissa bits of
+//    the key, so the running minimum is one LOP3 (immediate) + one VIMNMX per sphere
+//    (compare/select ops are half-rate on B200).  Cost: t is truncated by < 2^-19
+//    relative, towards the ray origin.  Equal keys fall to the lower list position.
+//  - generic shape: run-time counts, geometry from global memory (any scene size).
+template<class Shape>
 __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists const& gl, PathF32 const& p,
                                             RayTerms const& r, float& t_out, int& id_out)
 {
     uint32_t best = kNoHitBits;
     int id = -1;
-    if constexpr(NS >= 0) {
-        // The ORIGINAL sphere index rides in the low kIdBits mantissa bits of the key, so the
-        // running minimum is one LOP3 + one VIMNMX per sphere (compare/select ops are
-        // half-rate on B200) and equal keys fall to the lowest index, the reference's tie rule
-        // (main.cpp:35).  Cost: t is truncated by < 2^-19 relative, towards the ray origin.
-        static_assert(NS + NB <= (1 << kIdBits), "index does not fit the key");
-        uint32_t const keep = ~((1u << kIdBits) - 1u);
+    if constexpr(!Shape::generic) {
+        static_assert(Shape::total <= (1 << kIdBits), "list position does not fit the key");
+        constexpr uint32_t keep = ~((1u << kIdBits) - 1u);
+        constexpr int NS = Shape::small_near + Shape::small_both;
+        constexpr int NB = Shape::big_near + Shape::big_both;
 #pragma unroll
         for(int i = 0; i < NS; ++i) {
-            best = min(best, (key_small(cs.small_geo[i], p, r) & keep) | static_cast<uint32_t>(cs.small_id[i]));
+            uint32_t const k = i < Shape::small_near ? key_small<false>(cs.small_geo[i], p, r)
+                                                     : key_small<true>(cs.small_geo[i], p, r);
+            best = min(best, (k & keep) | static_cast<uint32_t>(i));
         }
 #pragma unroll
         for(int i = 0; i < NB; ++i) {
-            best = min(best, (key_big(cs.big_geo[i], p, r) & keep) | static_cast<uint32_t>(cs.big_id[i]));
+            uint32_t const k = i < Shape::big_near ? key_big<false>(cs.big_geo[i], p, r)
+                                                   : key_big<true>(cs.big_geo[i], p, r);
+            best = min(best, (k & keep) | static_cast<uint32_t>(NS + i));
         }
         id = static_cast<int>(best & ~keep);
         best &= keep;
     }
     else {
-        int const ns = cs.n_small;
-        int const nb = cs.n_big;
+        int const nsn = cs.n_small_near, ns = cs.n_small;
+        int const nbn = cs.n_big_near, nb = cs.n_big;
 #pragma unroll 4
-        for(int i = 0; i < ns; ++i) {
-            uint32_t const k = key_small(gl.small_geo[i], p, r);
+        for(int i = 0; i < nsn; ++i) {
+            uint32_t const k = key_small<false>(gl.small_geo[i], p, r);
             if(k < best) {
                 best = k;
                 id = i;
             }
         }
-        if(id >= 0) {
-            id = gl.small_id[id];
-        }
-        int idb = -1;
-        for(int i = 0; i < nb; ++i) {
-            uint32_t const k = key_big(gl.big_geo[i], p, r);
+        for(int i = nsn; i < ns; ++i) {
+            uint32_t const k = key_small<true>(gl.small_geo[i], p, r);
             if(k < best) {
                 best = k;
-                idb = i;
+                id = i;
             }
         }
-        if(idb >= 0) {
-            id = gl.big_id[idb];
+        for(int i = 0; i < nbn; ++i) {
+            uint32_t const k = key_big<false>(gl.big_geo[i], p, r);
+            if(k < best) {
+                best = k;
+                id = ns + i;
+            }
+        }
+        for(int i = nbn; i < nb; ++i) {
+            uint32_t const k = key_big<true>(gl.big_geo[i], p, r);
+            if(k < best) {
+                best = k;
+                id = ns + i;
+            }
         }
     }
     id_out = id;
-    t_out = (__uint_as_float(best) + r.eps_a) * fast_rcp(r.a);
+    t_out = __uint_as_float(best) + r.eps;
     return best < kNoHitBits;
-}
-
-// Primary-hit probe only: same scan, returns the index.
-template<int NS, int NB>
-__device__ __forceinline__ int primary_hit_index(ConstSceneF32 const& cs, GeoLists const& gl, PathF32 const& p)
-{
-    RayTerms const r = ray_terms(p);
-    float t;
-    int id;
-    return closest_hit<NS, NB>(cs, gl, p, r, t, id) ? id : -1;
 }
 
 struct BounceCounters
@@ -251,9 +293,9 @@ struct BounceCounters
     uint32_t dielectric;
 };
 
-// specular_ray, main.cpp:60-67: mirror about the OUTWARD normal with the raw
-// direction; the reference then draws one uniform and multiplies it by
-// fuzziness = 0 -- the draw must still advance the stream.
+// specular_ray, main.cpp:60-67: mirror about the OUTWARD normal; the length of the
+// reference's direction is unchanged by it (p.len stays).  The reference then draws one
+// uniform and multiplies it by fuzziness = 0 -- the draw must still advance the stream.
 __device__ __forceinline__ void reflect_ray(PathF32& p, float nx, float ny, float nz)
 {
     float const dn2 = 2.0f * fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));
@@ -269,10 +311,10 @@ template<bool kCount>
 __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool hit, float t, int id,
                                              ShadePlanes const& sp, BounceCounters& cnt)
 {
+    (void)r;
     if(!hit) {
         // main.cpp:116-119 sky gradient on the unit direction
-        float const uy = p.dy * fast_rsqrt(r.a);
-        float const tt = 0.5f * (uy + 1.0f);
+        float const tt = 0.5f * (p.dy + 1.0f);
         float const omt = 1.0f - tt;
         p.er = fmaf(p.tr, fmaf(0.5f, tt, omt), p.er);
         p.eg = fmaf(p.tg, fmaf(0.7f, tt, omt), p.eg);
@@ -359,6 +401,7 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool
             p.dx = fmaf(ux, cu, fmaf(vx, cv, fx * cos_t));
             p.dy = fmaf(uy, cu, fmaf(vy, cv, fy * cos_t));
             p.dz = fmaf(uz, cu, fmaf(vz, cv, fz * cos_t));
+            p.len = 1.0f; // main.cpp:54-55 normalises the new direction
         }
         else {
             // dielectric_ray, main.cpp:69-97, refraction index 2.0
@@ -366,8 +409,7 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool
                 cnt.dielectric++;
             }
             float const ratio = front ? 0.5f : 2.0f;
-            float const inv_len = fast_rsqrt(r.a);
-            float const cos_t = fminf(fabsf(dn) * inv_len, 1.0f); // (-unit_d).normal, the normal faces the ray
+            float const cos_t = fminf(fabsf(dn), 1.0f); // (-unit_d).normal, the normal faces the ray
             float const sin_t = fast_sqrt(fmaxf(0.0f, fmaf(-cos_t, cos_t, 1.0f)));
             bool reflect = ratio * sin_t > 1.0f;
             if(!reflect) {
@@ -381,13 +423,14 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool
                 reflect_ray(p, nx, ny, nz);
             }
             else {
-                float const px = fmaf(fx, cos_t, p.dx * inv_len) * ratio;
-                float const py = fmaf(fy, cos_t, p.dy * inv_len) * ratio;
-                float const pz = fmaf(fz, cos_t, p.dz * inv_len) * ratio;
+                float const px = fmaf(fx, cos_t, p.dx) * ratio;
+                float const py = fmaf(fy, cos_t, p.dy) * ratio;
+                float const pz = fmaf(fz, cos_t, p.dz) * ratio;
                 float const par = -fast_sqrt(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
                 p.dx = fmaf(fx, par, px);
                 p.dy = fmaf(fy, par, py);
                 p.dz = fmaf(fz, par, pz);
+                p.len = 1.0f; // r_out_perp + r_out_parallel is a unit vector (main.cpp:93-96)
             }
         }
     }

@@ -16,7 +16,14 @@
 //               the cancellation-free form c'/(s - hb').  Needed for the R = 1e6
 //               "wall" spheres of box_scene.hpp:16-47, where oc.oc - r^2 has no
 //               correct digits in binary32.
-//   * shading data per ORIGINAL sphere index, four float4 planes.
+//   * inside each class the spheres that can only ever be hit at their NEAR root come
+//     first: an opaque sphere (diffuse / specular) that the camera lens lies outside of
+//     is never left from its inside, so the far-root branch of sphere.cpp:21-27 is dead
+//     for it; dielectric spheres and spheres containing the
+//     camera keep both roots;
+//   * "list position" = index into the concatenation [small near-only, small both,
+//     big near-only, big both].  Shading data is stored per LIST POSITION (four float4
+//     planes), `order[]` maps a list position back to the caller's sphere index.
 #pragma once
 
 #include <cstdint>
@@ -76,17 +83,19 @@ struct CameraF32
 struct ConstSceneF32
 {
     CameraF32 cam;
-    int n_small;
+    int n_small_near; // small spheres tested at the near root only
+    int n_small;      // all small spheres (near-only first)
+    int n_big_near;
     int n_big;
     int n_total;
-    int pad_;
+    int pad_[3];
     SmallGeo small_geo[kMaxConstSpheres];
     BigGeo big_geo[kMaxConstSpheres];
-    int small_id[kMaxConstSpheres];
-    int big_id[kMaxConstSpheres];
+    int order[2 * kMaxConstSpheres]; // list position -> original sphere index
 };
 
-// Shading planes (global memory; staged to shared memory when n <= kSmemShadeSpheres)
+// Shading planes, indexed by LIST POSITION (global memory; staged to shared memory when
+// n <= kSmemShadeSpheres)
 //   a = (-c/R xyz, 1/R)            outward normal = P * a.w + a.xyz
 //   b = (emission rgb, reflection as int bits)
 //   c = (color rgb, p = max(color))
@@ -104,8 +113,7 @@ struct GeoLists
 {
     SmallGeo const* small_geo;
     BigGeo const* big_geo;
-    int const* small_id;
-    int const* big_id;
+    int const* order; // list position -> original sphere index
 };
 
 } // namespace ptb
