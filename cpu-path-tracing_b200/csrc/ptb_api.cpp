@@ -56,6 +56,7 @@ struct ptb_context
     uint8_t* d_rgb8 = nullptr;
 
     DeviceCounters* d_counters = nullptr;
+    WavefrontBuffers wf{ nullptr, nullptr, nullptr, 0 };
     ptb_stats stats{};
 };
 
@@ -441,6 +442,9 @@ void ptb_destroy(ptb_context* ctx)
     cudaFree(ctx->d_rgb);
     cudaFree(ctx->d_rgb8);
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->wf.planes);
+    cudaFree(ctx->wf.words);
+    cudaFree(ctx->wf.counters);
     if(ctx->ev0 != nullptr) {
         cudaEventDestroy(ctx->ev0);
     }
@@ -617,8 +621,8 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
        (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
     }
-    if(variant == PTB_VARIANT_WAVEFRONT) {
-        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: the wavefront variant is not built yet");
+    if(variant == PTB_VARIANT_WAVEFRONT && precision == PTB_PRECISION_FP64) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: the wavefront variant exists in FP32 only");
     }
     if(static_cast<uint64_t>(first_sample) + samples_per_subpixel > 0xFFFFFFFFull) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: sample range overflows 32 bits");
@@ -628,7 +632,13 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         ctx->stats.last_render_ms = 0.0;
         return PTB_OK; // the reference renders a black image for spp < 4 (main.cpp:206)
     }
-    cudaStream_t const st = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    if(variant == PTB_VARIANT_WAVEFRONT && st == nullptr) {
+        // CUDA graphs cannot be captured on the legacy default stream: drain it and use the private one;
+        // ptb_render blocks until the work is done, so later work on the default stream is still ordered
+        PTB_CUDA(ctx, cudaStreamSynchronize(nullptr));
+        st = ctx->own_stream;
+    }
     uint64_t const key = seed_key(seed);
     int launches = 0;
 
@@ -670,7 +680,29 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         p.shade = shade_planes(ctx);
         p.geo = geo_lists(ctx);
         p.n_total = ctx->n;
-        PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches));
+        if(variant == PTB_VARIANT_WAVEFRONT) {
+            uint64_t const items = static_cast<uint64_t>(p.nslots) * p.samples;
+            uint32_t const pool = static_cast<uint32_t>(std::min<uint64_t>(1ull << 22, std::max<uint64_t>(items, 1024)));
+            if(ctx->wf.pool < pool) {
+                cudaFree(ctx->wf.planes);
+                cudaFree(ctx->wf.words);
+                ctx->wf.planes = nullptr;
+                ctx->wf.words = nullptr;
+                ctx->wf.pool = 0;
+                PTB_CUDA(ctx, cudaMalloc(&ctx->wf.planes, kWfPlanesPerPool * static_cast<size_t>(pool) * sizeof(float4)));
+                PTB_CUDA(ctx, cudaMalloc(&ctx->wf.words, kWfWordsPerPool * static_cast<size_t>(pool) * sizeof(uint32_t)));
+                if(ctx->wf.counters == nullptr) {
+                    PTB_CUDA(ctx, cudaMalloc(&ctx->wf.counters, sizeof(WavefrontCounters)));
+                }
+                ctx->wf.pool = pool;
+            }
+            WavefrontBuffers buf = ctx->wf;
+            buf.pool = pool;
+            PTB_CUDA(ctx, launch_wavefront(buf, p, ctx->counts, ctx->sm_count, st, &launches));
+        }
+        else {
+            PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches));
+        }
     }
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     PTB_CUDA(ctx, cudaStreamSynchronize(st));

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
             int id;
             bool const hit = closest_hit<Shape>(c_scene, prm.geo, p, r, t, id);
             cnt.rays++;
-            alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
+            alive = shade_bounce<true>(p, hit, t, id, sp, cnt);
             if(!alive) {
                 red_add_v4(prm.accum + slot, p.er, p.eg, p.eb, 1.0f);
             }
@@ -280,6 +280,12 @@ cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, in
     return launch_one<GenericShape, false>(p, sm_count, stream);
 }
 
+} // namespace ptb
+
+#include "ptb_wavefront.cuh"
+
+namespace ptb {
+
 // ---- FP32 probe ---------------------------------------------------------------------------------
 // One thread per requested sample; same device functions AND the same (n_small, n_big)
 // specialisation as the megakernel, so the probe traces what the renderer traces.
@@ -319,7 +325,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         float t;
         int id;
         bool const hit = closest_hit<Shape>(c_scene, geo, p, r, t, id);
-        alive = shade_bounce<true>(p, r, hit, t, id, sp, cnt);
+        alive = shade_bounce<true>(p, hit, t, id, sp, cnt);
     }
     q.radiance[3 * i + 0] = p.er;
     q.radiance[3 * i + 1] = p.eg;

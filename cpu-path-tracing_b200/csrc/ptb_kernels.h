@@ -55,6 +55,30 @@ bool megakernel_has_specialisation(int small_near, int small_both, int big_near,
 cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
                               int* launches);
 
+// ---- wavefront / material-sorted variant (ptb_wavefront.cuh) ------------------------------------------
+struct WavefrontCounters
+{
+    uint32_t n_active[2];
+    uint32_t n_mat[2];
+    uint32_t regen_base;
+    uint32_t regen_count;
+    uint32_t iterations;
+    uint32_t pad_;
+    unsigned long long cursor;      // next (sample, slot) item
+    unsigned long long regen_item0;
+};
+constexpr int kWfPlanesPerPool = 18; // 2 active streams x 4 planes + 2 material streams x 5 planes
+constexpr int kWfWordsPerPool = 4;   // one slot array per stream
+struct WavefrontBuffers
+{
+    float4* planes;   // kWfPlanesPerPool * pool float4
+    uint32_t* words;  // kWfWordsPerPool * pool words
+    WavefrontCounters* counters;
+    uint32_t pool;
+};
+cudaError_t launch_wavefront(WavefrontBuffers const& buf, RenderParamsF32 const& p, SceneCounts const& c, int sm_count,
+                             cudaStream_t stream, int* launches);
+
 struct ProbeParams
 {
     uint64_t key;

@@ -305,13 +305,16 @@ __device__ __forceinline__ void reflect_ray(PathF32& p, float nx, float ny, floa
     (void)rng_next32(p.rng);
 }
 
-// One iteration of the bounce loop of main.cpp:111-155 AFTER the closest-hit query.
+// ---- one iteration of the bounce loop of main.cpp:111-155 AFTER the closest-hit query ----------
+// Split in two so that the wavefront variant can run the halves in different kernels:
+//   shade_common : sky on a miss, hit record, emission, Russian roulette, throughput
+//   scatter_*    : the three material functions of main.cpp:141-154
+
 // Returns true while the path is alive; on false p.er/eg/eb hold the path's radiance.
-template<bool kCount>
-__device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool hit, float t, int id,
-                                             ShadePlanes const& sp, BounceCounters& cnt)
+// On true: p.o = hit point, (nx,ny,nz) = outward normal, refl = material tag.
+__device__ __forceinline__ bool shade_common(PathF32& p, bool hit, float t, int id, ShadePlanes const& sp, float& nx,
+                                             float& ny, float& nz, int& refl)
 {
-    (void)r;
     if(!hit) {
         // main.cpp:116-119 sky gradient on the unit direction
         float const tt = 0.5f * (p.dy + 1.0f);
@@ -329,9 +332,9 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool
     float const hx = fmaf(p.dx, t, p.ox);
     float const hy = fmaf(p.dy, t, p.oy);
     float const hz = fmaf(p.dz, t, p.oz);
-    float const nx = fmaf(hx, sa.w, sa.x); // outward normal (P - c)/R
-    float const ny = fmaf(hy, sa.w, sa.y);
-    float const nz = fmaf(hz, sa.w, sa.z);
+    nx = fmaf(hx, sa.w, sa.x); // outward normal (P - c)/R
+    ny = fmaf(hy, sa.w, sa.y);
+    nz = fmaf(hz, sa.w, sa.z);
 
     // main.cpp:126
     p.er = fmaf(p.tr, sb.x, p.er);
@@ -357,8 +360,84 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool
     p.ox = hx;
     p.oy = hy;
     p.oz = hz;
+    refl = __float_as_int(sb.w);
+    return true;
+}
 
-    int const refl = __float_as_int(sb.w);
+// diffuse_ray, main.cpp:44-58: cosine-weighted about the FRONT-FACING normal (fx,fy,fz)
+__device__ __forceinline__ void scatter_diffuse(PathF32& p, float fx, float fy, float fz)
+{
+    float const u1 = rng_uniform_f32(p.rng);
+    float const u2 = rng_uniform_f32(p.rng);
+    float sphi, cphi;
+    __sincosf(6.283185307179586f * u1, &sphi, &cphi);
+    float const sin_t = fast_sqrt(u2);
+    float const cos_t = fast_sqrt(1.0f - u2);
+    // u = norm((|w.x| > 0.1 ? (0,1,0) : (1,0,0)) x w), v = w x u
+    float ux, uy, uz;
+    if(fabsf(fx) > 0.1f) {
+        float const inv = fast_rsqrt(fmaf(fz, fz, fx * fx));
+        ux = fz * inv;
+        uy = 0.0f;
+        uz = -fx * inv;
+    }
+    else {
+        float const inv = fast_rsqrt(fmaf(fz, fz, fy * fy));
+        ux = 0.0f;
+        uy = -fz * inv;
+        uz = fy * inv;
+    }
+    float const vx = fy * uz - fz * uy;
+    float const vy = fz * ux - fx * uz;
+    float const vz = fx * uy - fy * ux;
+    float const cu = cphi * sin_t, cv = sphi * sin_t;
+    p.dx = fmaf(ux, cu, fmaf(vx, cv, fx * cos_t));
+    p.dy = fmaf(uy, cu, fmaf(vy, cv, fy * cos_t));
+    p.dz = fmaf(uz, cu, fmaf(vz, cv, fz * cos_t));
+    p.len = 1.0f; // main.cpp:54-55 normalises the new direction
+}
+
+// dielectric_ray, main.cpp:69-97, refraction index 2.0; (nx,ny,nz) outward normal, dn = n.d
+__device__ __forceinline__ void scatter_dielectric(PathF32& p, float nx, float ny, float nz, float dn)
+{
+    bool const front = dn < 0.0f; // hit_record.cpp:7
+    float const fx = front ? nx : -nx, fy = front ? ny : -ny, fz = front ? nz : -nz;
+    float const ratio = front ? 0.5f : 2.0f;
+    float const cos_t = fminf(fabsf(dn), 1.0f); // (-unit_d).normal, the normal faces the ray
+    float const sin_t = fast_sqrt(fmaxf(0.0f, fmaf(-cos_t, cos_t, 1.0f)));
+    bool reflect = ratio * sin_t > 1.0f;
+    if(!reflect) {
+        // Schlick, r0 = ((1-n)/(1+n))^2 = 1/9 for n = 2 and n = 1/2 alike
+        float const m = 1.0f - cos_t;
+        float const m2 = m * m;
+        float const refl_prob = fmaf(8.0f / 9.0f, m2 * m2 * m, 1.0f / 9.0f);
+        reflect = refl_prob > rng_uniform_f32(p.rng);
+    }
+    if(reflect) {
+        reflect_ray(p, nx, ny, nz);
+    }
+    else {
+        float const px = fmaf(fx, cos_t, p.dx) * ratio;
+        float const py = fmaf(fy, cos_t, p.dy) * ratio;
+        float const pz = fmaf(fz, cos_t, p.dz) * ratio;
+        float const par = -fast_sqrt(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
+        p.dx = fmaf(fx, par, px);
+        p.dy = fmaf(fy, par, py);
+        p.dz = fmaf(fz, par, pz);
+        p.len = 1.0f; // r_out_perp + r_out_parallel is a unit vector (main.cpp:93-96)
+    }
+}
+
+// Both halves back to back: what the megakernel and the probe run.
+template<bool kCount>
+__device__ __forceinline__ bool shade_bounce(PathF32& p, bool hit, float t, int id, ShadePlanes const& sp,
+                                             BounceCounters& cnt)
+{
+    float nx, ny, nz;
+    int refl;
+    if(!shade_common(p, hit, t, id, sp, nx, ny, nz, refl)) {
+        return false;
+    }
     if(refl == 1) {
         if(kCount) {
             cnt.specular++;
@@ -367,74 +446,20 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, RayTerms const& r, bool
     }
     else {
         float const dn = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));
-        bool const front = dn < 0.0f; // hit_record.cpp:7
-        float const fx = front ? nx : -nx, fy = front ? ny : -ny, fz = front ? nz : -nz;
         if(refl == 0) {
-            // diffuse_ray, main.cpp:44-58
             if(kCount) {
                 cnt.diffuse++;
             }
-            float const u1 = rng_uniform_f32(p.rng);
-            float const u2 = rng_uniform_f32(p.rng);
-            float sphi, cphi;
-            __sincosf(6.283185307179586f * u1, &sphi, &cphi);
-            float const sin_t = fast_sqrt(u2);
-            float const cos_t = fast_sqrt(1.0f - u2);
-            // u = norm((|w.x| > 0.1 ? (0,1,0) : (1,0,0)) x w), v = w x u
-            float ux, uy, uz;
-            if(fabsf(fx) > 0.1f) {
-                float const inv = fast_rsqrt(fmaf(fz, fz, fx * fx));
-                ux = fz * inv;
-                uy = 0.0f;
-                uz = -fx * inv;
-            }
-            else {
-                float const inv = fast_rsqrt(fmaf(fz, fz, fy * fy));
-                ux = 0.0f;
-                uy = -fz * inv;
-                uz = fy * inv;
-            }
-            float const vx = fy * uz - fz * uy;
-            float const vy = fz * ux - fx * uz;
-            float const vz = fx * uy - fy * ux;
-            float const cu = cphi * sin_t, cv = sphi * sin_t;
-            p.dx = fmaf(ux, cu, fmaf(vx, cv, fx * cos_t));
-            p.dy = fmaf(uy, cu, fmaf(vy, cv, fy * cos_t));
-            p.dz = fmaf(uz, cu, fmaf(vz, cv, fz * cos_t));
-            p.len = 1.0f; // main.cpp:54-55 normalises the new direction
+            bool const front = dn < 0.0f; // hit_record.cpp:7
+            scatter_diffuse(p, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
         }
         else {
-            // dielectric_ray, main.cpp:69-97, refraction index 2.0
             if(kCount) {
                 cnt.dielectric++;
             }
-            float const ratio = front ? 0.5f : 2.0f;
-            float const cos_t = fminf(fabsf(dn), 1.0f); // (-unit_d).normal, the normal faces the ray
-            float const sin_t = fast_sqrt(fmaxf(0.0f, fmaf(-cos_t, cos_t, 1.0f)));
-            bool reflect = ratio * sin_t > 1.0f;
-            if(!reflect) {
-                // Schlick, r0 = ((1-n)/(1+n))^2 = 1/9 for n = 2 and n = 1/2 alike
-                float const m = 1.0f - cos_t;
-                float const m2 = m * m;
-                float const refl_prob = fmaf(8.0f / 9.0f, m2 * m2 * m, 1.0f / 9.0f);
-                reflect = refl_prob > rng_uniform_f32(p.rng);
-            }
-            if(reflect) {
-                reflect_ray(p, nx, ny, nz);
-            }
-            else {
-                float const px = fmaf(fx, cos_t, p.dx) * ratio;
-                float const py = fmaf(fy, cos_t, p.dy) * ratio;
-                float const pz = fmaf(fz, cos_t, p.dz) * ratio;
-                float const par = -fast_sqrt(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
-                p.dx = fmaf(fx, par, px);
-                p.dy = fmaf(fy, par, py);
-                p.dz = fmaf(fz, par, pz);
-                p.len = 1.0f; // r_out_perp + r_out_parallel is a unit vector (main.cpp:93-96)
-            }
+            scatter_dielectric(p, nx, ny, nz, dn);
         }
     }
-
     p.depth++;
     return p.depth < kDepthLimit; // main.cpp:111
 }

@@ -46,9 +46,10 @@ for name, W, H, S in [("box_mirror", 1920, 1080, 16), ("box_mirror", 1920, 1080,
     cam = pkg.camera_with_config(cfg)
     with pkg.Renderer(0) as r:
         r.upload_scene(sph); r.set_camera(cam); r.set_image(W, H, 2)
-        r.render(1, 0, 4)
-        r.clear()
-        r.render(1, 0, S); st = r.stats()
-        paths = W * H * 4 * S
-        print(f"TIMING {name} {W}x{H} samps/subpixel {S}: {st.last_render_ms:.2f} ms  {paths/st.last_render_ms/1e3:.1f} Mpaths/s "
-              f"{st.rays/st.last_render_ms/1e3:.1f} Mrays/s rays/path {st.rays/paths:.3f}")
+        for vname, flag in (("mega", pkg.VARIANT_MEGAKERNEL), ("wave", pkg.VARIANT_WAVEFRONT)):
+            r.render(1, 0, 4, flag)
+            r.clear()
+            r.render(1, 0, S, flag); st = r.stats()
+            paths = W * H * 4 * S
+            print(f"TIMING {vname} {name} {W}x{H} samps/subpixel {S}: {st.last_render_ms:.2f} ms  {paths/st.last_render_ms/1e3:.1f} Mpaths/s "
+                  f"{st.rays/st.last_render_ms/1e3:.1f} Mrays/s rays/path {st.rays/paths:.3f}")

@@ -163,6 +163,44 @@ def test_fp32_image_rmse_within_monte_carlo_noise(gpu, oracle_port):
         assert rmse <= bound, f"channel {c}: RMSE {rmse:.4g} > noise bound {bound:.4g}"
 
 
+# ---- the wavefront / material-sorted variant traces the same paths --------------------------------------------------------
+@pytest.mark.parametrize("name", SCENES)
+def test_wavefront_variant_matches_megakernel(gpu, oracle_port, name):
+    W, H, S = 192, 108, 12
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    ref = oracle_port.render(sph, cam, W, H, S, 2, 23, 0)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(23, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL)
+        mega = r.download_accum()
+        st_m = r.stats()
+        r.clear()
+        r.render(23, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_WAVEFRONT)
+        wave = r.download_accum()
+        st_w = r.stats()
+        img = r.resolve()
+    assert np.all(mega[:, 3] == S) and np.all(wave[:, 3] == S)
+    assert st_w.paths == st_m.paths and abs(st_w.rays - st_m.rays) <= 1e-3 * st_m.rays
+    close = np.isclose(mega[:, :3], wave[:, :3], rtol=1e-4, atol=1e-4).all(axis=1)
+    assert close.mean() > 0.995  # same arithmetic, same uniforms: only summation order and a few chaotic paths differ
+    assert np.abs(img - ref).mean() < 2e-3
+
+
+def test_wavefront_small_and_progressive(gpu):
+    W, H = 9, 7  # fewer items than one block of the pool
+    sph, cfg = gpu.builtin_scene("box", W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(3, 0, 2, gpu.VARIANT_WAVEFRONT)
+        r.render(3, 2, 3, gpu.VARIANT_WAVEFRONT)
+        a = r.download_accum()
+        r.clear()
+        r.render(3, 0, 5, gpu.VARIANT_MEGAKERNEL)
+        b = r.download_accum()
+    assert np.all(a[:, 3] == 5) and np.all(b[:, 3] == 5)
+    assert np.isclose(a[:, :3], b[:, :3], rtol=1e-4, atol=1e-4).all(axis=1).mean() > 0.97
+
+
 # ---- semantics that must survive the boundary ------------------------------------------------------
 def test_progressive_accumulation_and_sample_split(gpu):
     """render(0,8) == render(0,3) + render(3,5): what lets ranks split the samples of a sub-pixel."""
