@@ -104,6 +104,7 @@ _ptb_accum_buffer = _sig("ptb_accum_buffer", ctypes.c_int, _vp, ctypes.POINTER(_
 _ptb_set_accum_buffer = _sig("ptb_set_accum_buffer", ctypes.c_int, _vp, _vp, _sz)
 _ptb_download_accum = _sig("ptb_download_accum", ctypes.c_int, _vp, _vp, _sz)
 _ptb_get_stats = _sig("ptb_get_stats", ctypes.c_int, _vp, ctypes.POINTER(_Stats))
+_ptb_scene_layout = _sig("ptb_scene_layout", ctypes.c_int, _vp, _vp)
 _ptb_trace_samples = _sig("ptb_trace_samples", ctypes.c_int, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp,
                           _vp, _vp)
 _ptb_rng_draws = _sig("ptb_rng_draws", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, ctypes.c_int, _vp)
@@ -117,7 +118,7 @@ EXPORTED_SYMBOLS = (
     "ptb_abi_version", "ptb_device_count", "ptb_last_error", "ptb_create", "ptb_destroy", "ptb_set_stream",
     "ptb_reset_stream", "ptb_synchronize", "ptb_upload_scene", "ptb_set_camera", "ptb_set_image", "ptb_clear", "ptb_render",
     "ptb_resolve", "ptb_resolve_rgb8", "ptb_resolve_device", "ptb_measure_fp32_peak", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
-    "ptb_get_stats", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
+    "ptb_get_stats", "ptb_scene_layout", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
     "ptb_write_ppm",
 )
 
@@ -304,6 +305,13 @@ class Renderer:
         s = _Stats()
         self._check(_ptb_get_stats(self._ctx, ctypes.byref(s)))
         return Stats(*[getattr(s, f[0]) for f in _Stats._fields_])
+
+    def scene_layout(self) -> dict:
+        out = np.zeros(10, dtype=np.int32)
+        self._check(_ptb_scene_layout(self._ctx, _ptr(out)))
+        keys = ("small_near", "small_both", "big_near", "big_both", "big_x", "big_y", "big_z", "uniform_k", "fits_const",
+                "specialised")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def trace_samples(self, seed, xs, ys, sxs, sys_, samples, flags=PRECISION_FP64):
         arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, sxs, sys_, samples)]

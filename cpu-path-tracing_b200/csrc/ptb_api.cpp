@@ -36,7 +36,7 @@ struct ptb_context
     RawCamera* d_camera = nullptr;
     ConstSceneF32 cs{};
     double shift[3] = { 0, 0, 0 };
-    SceneCounts counts{ 0, 0, 0, 0, true };
+    SceneCounts counts{};
     SmallGeo* d_small = nullptr;
     BigGeo* d_big = nullptr;
     int* d_order = nullptr;
@@ -95,36 +95,64 @@ float4* active_accum(ptb_context* ctx)
 // epsilon = 1e-4 (constants.hpp:7), so R > 32 moves to the stable form.
 constexpr double kBigRadius = 32.0;
 
-// Build the FP32 scene: origin shift, class split, FP64-precomputed coefficients.
+// Choose the frame of the FP32 scene.  Default origin: centroid of the ordinary-sized spheres
+// (the region rays live in), so binary32 coordinates stay O(scene extent).  Refinement: if, on
+// some axis, every big sphere that does NOT extend along that axis has the same coordinate
+// (true for the five R = 1e6 walls of the box scenes, whose centres all lie on the three lines
+// through (0, 0, -1)), use that coordinate instead: those centres then lie exactly ON the frame
+// axes and take the one-component test (key_big_axis).
 void pack_scene(ptb_context* ctx)
 {
     int const n = ctx->n;
     std::vector<RawSphere> const& s = ctx->h_spheres;
 
-    // origin shift = centroid of the ordinary-sized spheres (the region rays live in)
-    double cx = 0, cy = 0, cz = 0;
+    double c[3] = { 0, 0, 0 };
     int m = 0;
     for(int i = 0; i < n; ++i) {
         if(s[i].radius <= kBigRadius) {
-            cx += s[i].px;
-            cy += s[i].py;
-            cz += s[i].pz;
+            c[0] += s[i].px;
+            c[1] += s[i].py;
+            c[2] += s[i].pz;
             ++m;
         }
     }
     if(m > 0) {
-        cx /= m;
-        cy /= m;
-        cz /= m;
+        for(double& v : c) {
+            v /= m;
+        }
     }
     else if(ctx->have_camera) {
-        cx = ctx->h_camera.pos[0];
-        cy = ctx->h_camera.pos[1];
-        cz = ctx->h_camera.pos[2];
+        for(int a = 0; a < 3; ++a) {
+            c[a] = ctx->h_camera.pos[a];
+        }
     }
-    ctx->shift[0] = cx;
-    ctx->shift[1] = cy;
-    ctx->shift[2] = cz;
+    for(int a = 0; a < 3; ++a) {
+        bool have = false, same = true;
+        double v = 0.0;
+        for(int i = 0; i < n; ++i) {
+            if(s[i].radius <= kBigRadius) {
+                continue;
+            }
+            double const coord = a == 0 ? s[i].px : (a == 1 ? s[i].py : s[i].pz);
+            if(std::fabs(coord) >= 1e-3 * s[i].radius) {
+                continue; // the sphere extends along this axis
+            }
+            if(!have) {
+                v = coord;
+                have = true;
+            }
+            else if(coord != v) {
+                same = false;
+            }
+        }
+        // only if the candidate keeps the frame near the action
+        if(have && same && std::fabs(v - c[a]) <= 4.0 * kBigRadius) {
+            c[a] = v;
+        }
+    }
+    ctx->shift[0] = c[0];
+    ctx->shift[1] = c[1];
+    ctx->shift[2] = c[2];
 }
 
 struct PackedScene
@@ -133,7 +161,7 @@ struct PackedScene
     std::vector<BigGeo> big_geo;     // near-only first, then both-roots
     std::vector<int> order;          // list position -> original index
     std::vector<float4> shade;       // 4 planes, by list position
-    SceneCounts counts{ 0, 0, 0, 0, true };
+    SceneCounts counts{};
 };
 
 // A sphere can only ever be hit at its NEAR root when no ray origin can lie inside it:
@@ -157,17 +185,45 @@ PackedScene pack_geometry(ptb_context* ctx)
     double const* sh = ctx->shift;
     PackedScene out;
 
-    // list order: [small near-only, small both, big near-only, big both], original order inside each
+    // list order: [small near-only, small both, big near-only (x-axis, y-axis, z-axis, other), big both],
+    // original order inside each
     std::vector<int> lists[4];
+    std::vector<int> big_near[4]; // x, y, z, other
+    double k_first = 0.0;
+    bool uniform_k = true, any_big = false;
     for(int i = 0; i < n; ++i) {
         bool const big = s[i].radius > kBigRadius;
         bool const near_only = near_root_only(s[i], ctx->h_camera, ctx->have_camera);
-        lists[(big ? 2 : 0) + (near_only ? 0 : 1)].push_back(i);
+        if(big) {
+            double const k = 1.0 / (2.0 * s[i].radius);
+            if(!any_big) {
+                k_first = k;
+                any_big = true;
+            }
+            else if(k != k_first) {
+                uniform_k = false;
+            }
+        }
+        if(big && near_only) {
+            double const x = s[i].px - sh[0], y = s[i].py - sh[1], z = s[i].pz - sh[2];
+            int const axis = (y == 0.0 && z == 0.0) ? 0 : ((x == 0.0 && z == 0.0) ? 1 : ((x == 0.0 && y == 0.0) ? 2 : 3));
+            big_near[axis].push_back(i);
+        }
+        else {
+            lists[(big ? 2 : 0) + (near_only ? 0 : 1)].push_back(i);
+        }
+    }
+    for(auto const& l : big_near) {
+        lists[2].insert(lists[2].end(), l.begin(), l.end());
     }
     out.counts.small_near = static_cast<int>(lists[0].size());
     out.counts.small_both = static_cast<int>(lists[1].size());
     out.counts.big_near = static_cast<int>(lists[2].size());
     out.counts.big_both = static_cast<int>(lists[3].size());
+    out.counts.big_x = static_cast<int>(big_near[0].size());
+    out.counts.big_y = static_cast<int>(big_near[1].size());
+    out.counts.big_z = static_cast<int>(big_near[2].size());
+    out.counts.uniform_k = any_big && uniform_k;
     out.counts.fits_const = out.counts.small_near + out.counts.small_both <= kMaxConstSpheres &&
                             out.counts.big_near + out.counts.big_both <= kMaxConstSpheres;
     for(auto const& l : lists) {
@@ -876,6 +932,21 @@ int ptb_get_stats(ptb_context* ctx, ptb_stats* out)
     ctx->stats.hits_specular = c.specular;
     ctx->stats.hits_dielectric = c.dielectric;
     *out = ctx->stats;
+    return PTB_OK;
+}
+
+int ptb_scene_layout(ptb_context* ctx, int32_t out[10])
+{
+    if(ctx == nullptr || out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(!ctx->have_scene) {
+        return fail(ctx, PTB_ERR_STATE, "no scene: call ptb_upload_scene first");
+    }
+    SceneCounts const& c = ctx->counts;
+    int32_t const v[10] = { c.small_near, c.small_both, c.big_near, c.big_both, c.big_x, c.big_y, c.big_z,
+                            c.uniform_k ? 1 : 0, c.fits_const ? 1 : 0, megakernel_has_specialisation(c) ? 1 : 0 };
+    std::memcpy(out, v, sizeof(v));
     return PTB_OK;
 }
 

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
 
         // ---- one bounce ---------------------------------------------------------------------------
         if(alive) {
-            RayTerms const r = ray_terms(p);
+            RayTerms const r = ray_terms(p, Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f);
             float t;
             int id;
             bool const hit = closest_hit<Shape>(c_scene, prm.geo, p, r, t, id);
@@ -214,18 +214,23 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
 // (small near-only, small both-roots, big near-only, big both-roots) list lengths with a fully
 // unrolled kernel.  Everything else runs the generic run-time-count variant.
 #define PTB_MEGA_SPECIALISATIONS(X) \
-    X(2, 1, 5, 0) /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball, glass ball, 5 R=1e6 walls */ \
-    X(3, 1, 1, 0) /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100)                    */ \
-    X(2, 2, 1, 0) /* depth-of-field scene (BASELINE config 4): two glass spheres                        */ \
-    X(0, 3, 0, 5) /* box scenes with the camera inside a sphere / all-both fallback                     */ \
-    X(1, 0, 0, 0) \
-    X(0, 1, 0, 0) \
-    X(8, 0, 0, 0)
+    X(2, 1, 5, 0, 2, 2, 1, true)  /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball | glass ball | 5 R=1e6 walls on the frame axes */ \
+    X(3, 1, 1, 0, 0, 1, 0, true)  /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100, on the y axis)                       */ \
+    X(2, 2, 1, 0, 0, 1, 0, true)  /* depth-of-field scene (BASELINE config 4): two glass spheres                                             */ \
+    X(2, 1, 5, 0, 0, 0, 0, false) /* box scenes in a frame where the walls are not axis spheres                                             */ \
+    X(0, 3, 0, 5, 0, 0, 0, false) /* box scenes with the camera inside every sphere's reach: all both-roots                                 */ \
+    X(1, 0, 0, 0, 0, 0, 0, false) \
+    X(0, 1, 0, 0, 0, 0, 0, false) \
+    X(8, 0, 0, 0, 0, 0, 0, false)
 
-bool megakernel_has_specialisation(int sn, int sb, int bn, int bb)
+#define PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk) \
+    ((c).small_near == (a) && (c).small_both == (b) && (c).big_near == (cc) && (c).big_both == (d) && (c).big_x == (bx) && \
+     (c).big_y == (by) && (c).big_z == (bz) && (c).uniform_k == (uk) && (c).fits_const)
+
+bool megakernel_has_specialisation(SceneCounts const& c)
 {
-#define X(a, b, c, d) \
-    if(sn == (a) && sb == (b) && bn == (c) && bb == (d)) { \
+#define X(a, b, cc, d, bx, by, bz, uk) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk)) { \
         return true; \
     }
     PTB_MEGA_SPECIALISATIONS(X)
@@ -268,9 +273,9 @@ cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, in
         *launches += 1;
     }
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d) \
-    if(c.small_near == (a) && c.small_both == (b) && c.big_near == (cc) && c.big_both == (d) && smem && c.fits_const) { \
-        return launch_one<SceneShape<(a), (b), (cc), (d)>, true>(p, sm_count, stream); \
+#define X(a, b, cc, d, bx, by, bz, uk) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk) && smem) { \
+        return launch_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk)>, true>(p, sm_count, stream); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X
@@ -311,7 +316,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         q.ray[6 * i + 5] = p.dz * p.len;
     }
     {
-        RayTerms const r0 = ray_terms(p);
+        RayTerms const r0 = ray_terms(p, Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f);
         float t0;
         int pos;
         bool const hit0 = closest_hit<Shape>(c_scene, geo, p, r0, t0, pos);
@@ -321,7 +326,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
     BounceCounters cnt{ 0, 0, 0, 0 };
     bool alive = true;
     while(alive) {
-        RayTerms const r = ray_terms(p);
+        RayTerms const r = ray_terms(p, Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f);
         float t;
         int id;
         bool const hit = closest_hit<Shape>(c_scene, geo, p, r, t, id);
@@ -343,9 +348,9 @@ cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePl
     }
     unsigned const threads = 128;
     unsigned const blocks = (p.count + threads - 1) / threads;
-#define X(a, b, cc, d) \
-    if(c.small_near == (a) && c.small_both == (b) && c.big_near == (cc) && c.big_both == (d) && c.fits_const) { \
-        probe_f32_kernel<SceneShape<(a), (b), (cc), (d)>><<<blocks, threads, 0, stream>>>(p, shade, geo); \
+#define X(a, b, cc, d, bx, by, bz, uk) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk)) { \
+        probe_f32_kernel<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk)>><<<blocks, threads, 0, stream>>>(p, shade, geo); \
         return cudaGetLastError(); \
     }
     PTB_MEGA_SPECIALISATIONS(X)

@@ -46,11 +46,13 @@ cudaError_t upload_const_scene(ConstSceneF32 const& cs, cudaStream_t stream);
 // Lengths of the four geometry lists of a packed scene (ptb_scene.cuh)
 struct SceneCounts
 {
-    int small_near, small_both, big_near, big_both;
-    bool fits_const; // both classes fit the __constant__ lists
+    int small_near = 0, small_both = 0, big_near = 0, big_both = 0;
+    bool fits_const = true; // both classes fit the __constant__ lists
+    int big_x = 0, big_y = 0, big_z = 0; // prefix of the near-only big list: centres on a frame axis
+    bool uniform_k = false;              // every big sphere has the same radius
 };
 // True when a fully unrolled kernel exists for these list lengths.
-bool megakernel_has_specialisation(int small_near, int small_both, int big_near, int big_both);
+bool megakernel_has_specialisation(SceneCounts const& c);
 // Launch the persistent megakernel: grid = SM count * resident blocks.
 cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
                               int* launches);

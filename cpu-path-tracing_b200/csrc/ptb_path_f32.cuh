@@ -140,9 +140,10 @@ struct RayTerms
     float od;    // o.d
     float oo;    // o.o
     float o2x, o2y, o2z; // 2*o
+    float kod, koo;      // k*od, k*oo for scenes whose big spheres share one radius (k = 1/2R)
 };
 
-__device__ __forceinline__ RayTerms ray_terms(PathF32 const& p)
+__device__ __forceinline__ RayTerms ray_terms(PathF32 const& p, float k_uniform = 0.0f)
 {
     RayTerms r;
     r.eps = kEpsilon * p.len;
@@ -151,6 +152,8 @@ __device__ __forceinline__ RayTerms ray_terms(PathF32 const& p)
     r.o2x = p.ox + p.ox;
     r.o2y = p.oy + p.oy;
     r.o2z = p.oz + p.oz;
+    r.kod = k_uniform * r.od;
+    r.koo = k_uniform * r.oo;
     return r;
 }
 
@@ -204,13 +207,38 @@ __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, R
     }
 }
 
-// Compile-time description of a scene's four geometry lists; all -1 = run-time counts.
-template<int SN, int SB, int BN, int BB>
+// Near-only big sphere whose centre lies ON a coordinate axis of the shifted frame (the host
+// picks the frame so that the R = 1e6 walls of the box scenes, whose centres all sit on the
+// three lines through (0,0,-1), qualify): g = -k c has a single non-zero component, so the two
+// 3-term dot products shrink to one FFMA each.  kUniformK: all big spheres share k = 1/2R, so
+// k*od and k*oo are per-ray values.  Exact -- nothing is approximated.
+template<int AXIS, bool kUniformK>
+__device__ __forceinline__ uint32_t key_big_axis(BigGeo const& b, PathF32 const& p, RayTerms const& r)
+{
+    float const da = AXIS == 0 ? p.dx : (AXIS == 1 ? p.dy : p.dz);
+    float const oa2 = AXIS == 0 ? r.o2x : (AXIS == 1 ? r.o2y : r.o2z);
+    float const ga = AXIS == 0 ? b.gx : (AXIS == 1 ? b.gy : b.gz);
+    float const hb = fmaf(da, ga, kUniformK ? r.kod : b.k * r.od);
+    float const cp = fmaf(oa2, ga, kUniformK ? r.koo + b.K : fmaf(b.k, r.oo, b.K));
+    float const disc = fmaf(hb, hb, -(b.k * cp));
+    float const m = disc_sqrt(disc) + fabsf(hb);
+    uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
+    float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
+    return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
+}
+
+// Compile-time description of a scene's geometry lists; SN < 0 = run-time counts.
+//   SN small near-only, SB small both-roots, BN big near-only (of which the first BX / BY / BZ
+//   are x- / y- / z-axis spheres), BB big both-roots, UK = big spheres share one radius.
+template<int SN, int SB, int BN, int BB, int BX = 0, int BY = 0, int BZ = 0, bool UK = false>
 struct SceneShape
 {
     static constexpr int small_near = SN, small_both = SB, big_near = BN, big_both = BB;
+    static constexpr int big_x = BX, big_y = BY, big_z = BZ;
+    static constexpr bool uniform_k = UK;
     static constexpr bool generic = SN < 0;
     static constexpr int total = SN + SB + BN + BB;
+    static_assert(SN < 0 || BX + BY + BZ <= BN, "axis spheres are a prefix of the near-only big list");
 };
 using GenericShape = SceneShape<-1, -1, -1, -1>;
 
@@ -240,8 +268,22 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
         }
 #pragma unroll
         for(int i = 0; i < NB; ++i) {
-            uint32_t const k = i < Shape::big_near ? key_big<false>(cs.big_geo[i], p, r)
-                                                   : key_big<true>(cs.big_geo[i], p, r);
+            uint32_t k;
+            if(i < Shape::big_x) {
+                k = key_big_axis<0, Shape::uniform_k>(cs.big_geo[i], p, r);
+            }
+            else if(i < Shape::big_x + Shape::big_y) {
+                k = key_big_axis<1, Shape::uniform_k>(cs.big_geo[i], p, r);
+            }
+            else if(i < Shape::big_x + Shape::big_y + Shape::big_z) {
+                k = key_big_axis<2, Shape::uniform_k>(cs.big_geo[i], p, r);
+            }
+            else if(i < Shape::big_near) {
+                k = key_big<false>(cs.big_geo[i], p, r);
+            }
+            else {
+                k = key_big<true>(cs.big_geo[i], p, r);
+            }
             best = min(best, (k & keep) | static_cast<uint32_t>(NS + i));
         }
         id = static_cast<int>(best & ~keep);

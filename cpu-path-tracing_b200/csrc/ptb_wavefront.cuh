@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kWfThreads) wf_extend_kernel(WavefrontState co
         float nx = 0.f, ny = 0.f, nz = 0.f, dn = 0.f;
         if(i < nactive) {
             wf_load(in, i, p, slot);
-            RayTerms const r = ray_terms(p);
+            RayTerms const r = ray_terms(p, Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f);
             float t;
             int id;
             bool const hit = closest_hit<Shape>(c_scene, prm.geo, p, r, t, id);
@@ -412,9 +412,9 @@ cudaError_t launch_wavefront(WavefrontBuffers const& buf, RenderParamsF32 const&
     w.ctr = buf.counters;
     w.pool = buf.pool;
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d) \
-    if(c.small_near == (a) && c.small_both == (b) && c.big_near == (cc) && c.big_both == (d) && smem && c.fits_const) { \
-        return wf_run<SceneShape<(a), (b), (cc), (d)>, true>(w, p, sm_count, stream, launches); \
+#define X(a, b, cc, d, bx, by, bz, uk) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk) && smem) { \
+        return wf_run<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk)>, true>(w, p, sm_count, stream, launches); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X

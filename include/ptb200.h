@@ -145,6 +145,12 @@ int ptb_download_accum(ptb_context* ctx, float* out, size_t floats);
 /* ---- introspection ------------------------------------------------------------------ */
 int ptb_get_stats(ptb_context* ctx, ptb_stats* out);
 
+/* How the FP32 path packed the uploaded scene (ptb_scene.cuh): out[0..9] = small near-only,
+ * small both-roots, big near-only, big both-roots, of the big near-only: on the x / y / z
+ * axis of the frame, big spheres share one radius (0/1), lists fit constant memory (0/1),
+ * a fully unrolled kernel exists for this layout (0/1). */
+int ptb_scene_layout(ptb_context* ctx, int32_t out[10]);
+
 /* Parity probe: trace `count` individual samples (x, y, sx, sy, sample index in
  * reference loop coordinates) and return, per sample, the sphere index hit by the
  * camera ray (-1 = miss) and the radiance estimate.  PTB_PRECISION_FP64 gives the

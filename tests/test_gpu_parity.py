@@ -314,6 +314,28 @@ def test_generic_kernel_for_unspecialised_scene(gpu, oracle_port):
     assert np.abs(img - ref).mean() < 1e-2
 
 
+def test_scene_layouts_take_the_specialised_kernels(gpu):
+    expect = {
+        "box": dict(small_near=2, small_both=1, big_near=5, big_both=0, big_x=2, big_y=2, big_z=1, uniform_k=1, specialised=1),
+        "box_mirror": dict(small_near=2, small_both=1, big_near=5, big_both=0, big_x=2, big_y=2, big_z=1, uniform_k=1, specialised=1),
+        "simple": dict(small_near=3, small_both=1, big_near=1, big_both=0, big_x=0, big_y=1, big_z=0, uniform_k=1, specialised=1),
+        "dof_glass": dict(small_near=2, small_both=2, big_near=1, big_both=0, big_x=0, big_y=1, big_z=0, uniform_k=1, specialised=1),
+        "spheres10k": dict(fits_const=0, specialised=0, big_near=1),
+    }
+    for name, want in expect.items():
+        sph, cfg = gpu.builtin_scene(name, 64, 48)
+        with make_renderer(gpu, sph, gpu.camera_with_config(cfg), 64, 48) as r:
+            got = r.scene_layout()
+        for k, v in want.items():
+            assert got[k] == v, (name, k, got)
+    # a camera INSIDE an opaque sphere keeps both roots for it
+    sph, cfg = gpu.builtin_scene("box", 64, 48)
+    sph = sph.copy()
+    sph["radius"][6] = 50.0  # the mirror ball now swallows the camera (and is "big")
+    with make_renderer(gpu, sph, gpu.camera_with_config(cfg), 64, 48) as r:
+        assert r.scene_layout()["big_both"] == 1
+
+
 def test_error_behaviour(gpu):
     with gpu.Renderer(0) as r:
         with pytest.raises(gpu.PtbError) as e:
