@@ -9,6 +9,8 @@ legs may import this module.  Two families of libraries share one call surface:
                                object code with the counter stream injected.
   * ``Oracle("ref_stock")`` -> oracle/_ref/libptref_stock.so, the reference's own
                                object code with its stock mt19937 stream.
+  * ``Oracle("ref_sandbox")`` -> oracle/_ref/libsbref.so, sandbox/main.cpp's own object
+                               code (the stand-alone smallpt fork).
 
 oracle/_ref/*.so can only be BUILT where /root/reference exists; the built files
 travel to the GPU box with the repo snapshot.
@@ -35,6 +37,7 @@ _PATHS = {
     "port": os.path.join(HERE, "libpt_oracle.so"),
     "ref_ctr": os.path.join(HERE, "_ref", "libptref_ctr.so"),
     "ref_stock": os.path.join(HERE, "_ref", "libptref_stock.so"),
+    "ref_sandbox": os.path.join(HERE, "_ref", "libsbref.so"),
 }
 
 _vp = ctypes.c_void_p
@@ -154,6 +157,61 @@ class Oracle:
         """Run the reference PROGRAM (src/main.cpp:199-248, built unmodified as
         oracle/_ref/cpu_path_tracer) in workdir -> workdir/image.ppm."""
         exe = os.path.join(HERE, "_ref", "cpu_path_tracer")
+        return subprocess.run([exe, str(int(spp))], cwd=workdir, stderr=subprocess.DEVNULL).returncode
+
+    # ---- sandbox/main.cpp, the stand-alone smallpt fork (port, ref_sandbox) -------------------------------
+    def sb_scene(self):
+        """(spheres[n,88] uint8, cam8 float64[8]) exactly as sandbox/main.cpp defines them."""
+        assert self.kind == "ref_sandbox"
+        sph = np.zeros((32, SPHERE_BYTES), dtype=np.uint8)
+        n = self.lib.sbref_scene(_ptr(sph), 32)
+        cam = np.zeros(8, dtype=np.float64)
+        self.lib.sbref_camera(_ptr(cam))
+        return sph[:n].copy(), cam
+
+    def sb_render(self, spheres, cam8, width, height, samps, mode=1, seed=1, first_sample=0, y0=0, y1=None, nthreads=0):
+        """mode 0: the program's erand48 stream (Xi = {0,0,y^3} per row); mode 1: counter stream."""
+        assert self.kind in ("port", "ref_sandbox")
+        y1 = height if y1 is None else y1
+        img = np.zeros((height, width, 3), dtype=np.float64)
+        args = [int(width), int(height), int(samps), int(mode), ctypes.c_uint64(seed), ctypes.c_uint32(first_sample),
+                int(y0), int(y1), _ptr(img), int(nthreads)]
+        if self.kind == "port":
+            spheres = np.ascontiguousarray(spheres).view(np.uint8).reshape(-1, SPHERE_BYTES)
+            cam8 = np.ascontiguousarray(cam8, dtype=np.float64)
+            self.lib.orc_sb_render(_ptr(spheres), len(spheres), _ptr(cam8), *args)
+        else:
+            self.lib.sbref_render(*args)
+        return img
+
+    def sb_samples(self, spheres, cam8, width, height, seed, xs, ys, sxs, sys_, samples):
+        assert self.kind in ("port", "ref_sandbox")
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, sxs, sys_, samples)]
+        count = arrs[0].size
+        hit = np.zeros(count, dtype=np.int32)
+        rad = np.zeros((count, 3), dtype=np.float64)
+        ray = np.zeros((count, 6), dtype=np.float64)
+        draws = np.zeros(count, dtype=np.uint64)
+        args = [int(width), int(height), ctypes.c_uint64(seed), *[_ptr(a) for a in arrs], int(count), _ptr(hit), _ptr(rad),
+                _ptr(ray), _ptr(draws)]
+        if self.kind == "port":
+            spheres = np.ascontiguousarray(spheres).view(np.uint8).reshape(-1, SPHERE_BYTES)
+            cam8 = np.ascontiguousarray(cam8, dtype=np.float64)
+            self.lib.orc_sb_samples(_ptr(spheres), len(spheres), _ptr(cam8), *args)
+        else:
+            self.lib.sbref_samples(*args)
+        return hit, rad, ray, draws
+
+    def sb_to_int(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.zeros(v.size, dtype=np.int32)
+        (self.lib.orc_sb_to_int if self.kind == "port" else self.lib.sbref_to_int)(_ptr(v), int(v.size), _ptr(out))
+        return out.reshape(v.shape)
+
+    @staticmethod
+    def sandbox_program(spp: int, workdir: str) -> int:
+        """Run the sandbox PROGRAM (oracle/_ref/smallpt, built as sandbox/run.sh:3) -> workdir/image.ppm."""
+        exe = os.path.join(HERE, "_ref", "smallpt")
         return subprocess.run([exe, str(int(spp))], cwd=workdir, stderr=subprocess.DEVNULL).returncode
 
     # ---- statistics (port only) -------------------------------------------------------

@@ -114,6 +114,18 @@ void orc_mt_render(void const* spheres, int n, void const* camera, int width, in
                    int num_subpixels, int seed_mode, uint32_t const* row_seed, int y0, int y1, double* image_out,
                    int nthreads);
 
+/* ---- sandbox/main.cpp (the stand-alone smallpt fork), pt_oracle_sandbox.c -------------------------
+ * cam8 = camera position(3), direction(3, un-normalised), field-of-view factor (.5135), push (140):
+ * the constants of sandbox/main.cpp:235-237,260.  mode 0 = the program's erand48 stream,
+ * 1 = counter stream.  Same signatures as sbref_render / sbref_samples in ref/sandbox_driver.cpp,
+ * plus the scene, which the sandbox keeps in a global array. */
+void orc_sb_render(void const* spheres, int n, double const* cam8, int w, int h, int samps, int mode, uint64_t seed,
+                   uint32_t first_sample, int y0, int y1, double* image_out, int nthreads);
+void orc_sb_samples(void const* spheres, int n, double const* cam8, int w, int h, uint64_t seed, uint32_t const* xs,
+                    uint32_t const* ys, uint32_t const* sxs, uint32_t const* sys, uint32_t const* samples, int count,
+                    int32_t* primary_hit, double* radiance_out, double* ray_out, uint64_t* draws_out);
+void orc_sb_to_int(double const* v, int n, int* out);
+
 #ifdef __cplusplus
 }
 #endif

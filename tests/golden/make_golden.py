@@ -16,6 +16,9 @@ Fixtures
   refmain_rows.npz  rows y%64==0 of image.ppm written by the reference PROGRAM (main.cpp:199-248,
                     1024x768 box_mirror, 4 spp): bit-reproducible because (unsigned short)(y^3)==0
   image_<s>.npz     small whole images + un-clamped per-sub-pixel sums with the counter stream
+  sandbox.npz       sandbox/main.cpp (stand-alone smallpt): its scene and camera constants, per-sample
+                    vectors from its own radiance() with the counter stream, small images in both streams,
+                    and 16 rows of the image.ppm its PROGRAM writes at 4 spp (deterministic: erand48)
 """
 import os
 import sys
@@ -83,6 +86,28 @@ def main():
     ys = np.arange(0, 768, 64)
     np.savez_compressed(os.path.join(HERE, "refmain_rows.npz"), spp=4, rows_y=ys,
                         rows=np.stack([px[768 - 1 - y] for y in ys]).astype(np.uint8))
+    # ---- sandbox/main.cpp (the stand-alone smallpt fork) ------------------------------------------------
+    sb = Oracle("ref_sandbox")
+    sph, cam8 = sb.sb_scene()
+    W, H, N = 200, 150, 4000
+    xs, ys = rng.integers(0, W, N), rng.integers(0, H, N)
+    sx, sy = rng.integers(0, 2, N), rng.integers(0, 2, N)
+    ss = rng.integers(0, 1 << 24, N)
+    hit, rad, ray, draws = sb.sb_samples(sph, cam8, W, H, 13, xs, ys, sx, sy, ss)
+    img_stock = sb.sb_render(sph, cam8, 96, 72, 2, mode=0)
+    img_ctr = sb.sb_render(sph, cam8, 96, 72, 3, mode=1, seed=21, first_sample=5)
+    with tempfile.TemporaryDirectory() as tmp:
+        assert sb.sandbox_program(4, tmp) == 0
+        with open(os.path.join(tmp, "image.ppm")) as f:
+            tok = f.read().split()
+    assert tok[:4] == ["P3", "1024", "768", "255"]
+    px = np.array(tok[4:], dtype=np.int32).reshape(768, 1024, 3)
+    rows = np.arange(0, 768, 48)
+    np.savez_compressed(os.path.join(HERE, "sandbox.npz"), spheres=sph, cam8=cam8, width=W, height=H, seed=13,
+                        x=xs.astype(np.uint32), y=ys.astype(np.uint32), sx=sx.astype(np.uint32), sy=sy.astype(np.uint32),
+                        sample=ss.astype(np.uint32), hit=hit, radiance=rad, ray=ray, draws=draws.astype(np.uint32),
+                        img_stock=img_stock, img_ctr=img_ctr, program_rows_y=rows,
+                        program_rows=np.stack([px[768 - 1 - y] for y in rows]).astype(np.uint8))
     print("golden fixtures written to", HERE)
 
 
