@@ -35,6 +35,8 @@ VARIANT_MEGAKERNEL = 0x0
 VARIANT_WAVEFRONT = 0x1
 PRECISION_FP32 = 0x00
 PRECISION_FP64 = 0x10
+INTEGRATOR_PT = 0x000
+INTEGRATOR_SMALLPT = 0x100
 
 DIFFUSE, SPECULAR, DIELECTRIC = 0, 1, 2
 
@@ -93,6 +95,7 @@ _ptb_reset_stream = _sig("ptb_reset_stream", ctypes.c_int, _vp)
 _ptb_synchronize = _sig("ptb_synchronize", ctypes.c_int, _vp)
 _ptb_upload_scene = _sig("ptb_upload_scene", ctypes.c_int, _vp, _vp, _sz, _sz)
 _ptb_set_camera = _sig("ptb_set_camera", ctypes.c_int, _vp, _vp, _sz)
+_ptb_set_smallpt_camera = _sig("ptb_set_smallpt_camera", ctypes.c_int, _vp, _vp)
 _ptb_set_image = _sig("ptb_set_image", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int)
 _ptb_clear = _sig("ptb_clear", ctypes.c_int, _vp)
 _ptb_render = _sig("ptb_render", ctypes.c_int, _vp, _u64, _u32, _u32, _u32)
@@ -112,6 +115,8 @@ _ptb_camera_with_config = _sig("ptb_camera_with_config", ctypes.c_int, _vp, _vp)
 _ptb_builtin_scene = _sig("ptb_builtin_scene", ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _vp, _sz,
                           ctypes.POINTER(_sz), _vp)
 _ptb_write_ppm = _sig("ptb_write_ppm", ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.c_int)
+_ptb_write_ppm_smallpt = _sig("ptb_write_ppm_smallpt", ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.c_int)
+_ptb_builtin_smallpt_scene = _sig("ptb_builtin_smallpt_scene", ctypes.c_int, _vp, _sz, ctypes.POINTER(_sz), _vp)
 
 # every symbol include/ptb200.h declares (tests check the header against this list and the .so)
 EXPORTED_SYMBOLS = (
@@ -119,7 +124,7 @@ EXPORTED_SYMBOLS = (
     "ptb_reset_stream", "ptb_synchronize", "ptb_upload_scene", "ptb_set_camera", "ptb_set_image", "ptb_clear", "ptb_render",
     "ptb_resolve", "ptb_resolve_rgb8", "ptb_resolve_device", "ptb_measure_fp32_peak", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
     "ptb_get_stats", "ptb_scene_layout", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
-    "ptb_write_ppm",
+    "ptb_write_ppm", "ptb_write_ppm_smallpt", "ptb_builtin_smallpt_scene", "ptb_set_smallpt_camera",
 )
 
 
@@ -169,6 +174,18 @@ def builtin_scene(name: str, width: int, height: int):
     return spheres, cfg
 
 
+def builtin_smallpt_scene():
+    """(spheres: SPHERE_DTYPE[10], cam8: float64[8]) of sandbox/main.cpp."""
+    n = _sz(0)
+    _ptb_builtin_smallpt_scene(None, 0, ctypes.byref(n), None)
+    spheres = np.zeros(n.value, dtype=SPHERE_DTYPE)
+    cam8 = np.zeros(8, dtype=np.float64)
+    rc = _ptb_builtin_smallpt_scene(_ptr(spheres), n.value, ctypes.byref(n), _ptr(cam8))
+    if rc != 0:
+        raise PtbError(rc, "ptb_builtin_smallpt_scene")
+    return spheres, cam8
+
+
 def camera_with_config(cfg: np.ndarray) -> np.ndarray:
     cfg = np.ascontiguousarray(cfg)
     assert cfg.nbytes == CAMERA_CONFIG_BYTES
@@ -179,11 +196,11 @@ def camera_with_config(cfg: np.ndarray) -> np.ndarray:
     return cam
 
 
-def write_ppm(path: str, rgb: np.ndarray) -> None:
+def write_ppm(path: str, rgb: np.ndarray, smallpt: bool = False) -> None:
     rgb = np.ascontiguousarray(rgb, dtype=np.float64)
     h, w, c = rgb.shape
     assert c == 3
-    rc = _ptb_write_ppm(os.fsencode(path), _ptr(rgb), w, h)
+    rc = (_ptb_write_ppm_smallpt if smallpt else _ptb_write_ppm)(os.fsencode(path), _ptr(rgb), w, h)
     if rc != 0:
         raise PtbError(rc, f"ptb_write_ppm({path})")
 
@@ -238,6 +255,11 @@ class Renderer:
     def set_camera(self, camera: np.ndarray):
         camera = np.ascontiguousarray(camera)
         self._check(_ptb_set_camera(self._ctx, _ptr(camera), camera.nbytes))
+
+    def set_smallpt_camera(self, cam8: np.ndarray):
+        cam8 = np.ascontiguousarray(cam8, dtype=np.float64)
+        assert cam8.size == 8
+        self._check(_ptb_set_smallpt_camera(self._ctx, _ptr(cam8)))
 
     def set_image(self, width: int, height: int, num_subpixels: int = 2):
         self._check(_ptb_set_image(self._ctx, width, height, num_subpixels))
@@ -309,9 +331,12 @@ class Renderer:
     def scene_layout(self) -> dict:
         out = np.zeros(10, dtype=np.int32)
         self._check(_ptb_scene_layout(self._ctx, _ptr(out)))
-        keys = ("small_near", "small_both", "big_near", "big_both", "big_x", "big_y", "big_z", "uniform_k", "fits_const",
+        keys = ("small_near", "small_both", "big_near", "big_both", "big_x", "big_y", "big_z", "bits", "fits_const",
                 "specialised")
-        return dict(zip(keys, [int(v) for v in out]))
+        d = dict(zip(keys, [int(v) for v in out]))
+        bits = d.pop("bits")
+        d["uniform_k"], d["embed_ok"] = bits & 1, (bits >> 1) & 1
+        return d
 
     def trace_samples(self, seed, xs, ys, sxs, sys_, samples, flags=PRECISION_FP64):
         arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, sxs, sys_, samples)]

@@ -34,6 +34,9 @@ struct ptb_context
     RawSphere* d_spheres = nullptr;
     size_t d_spheres_cap = 0;
     RawCamera* d_camera = nullptr;
+    double sb_cam8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // smallpt camera: position, direction, fov factor, push
+    bool have_sbcam = false;
+    double* d_sbcam8 = nullptr;
     ConstSceneF32 cs{};
     double shift[3] = { 0, 0, 0 };
     SceneCounts counts{};
@@ -168,14 +171,33 @@ struct PackedScene
 // it must be opaque (diffuse / specular scatter back to the outside, main.cpp:44-67) and the
 // camera lens (position +- the largest lens offset, camera.cpp:34-35: |rd*(s+t)| <= 2*sqrt(2)*lens_radius)
 // must be outside it.  Dielectric spheres are traversed from inside and keep both roots.
-bool near_root_only(RawSphere const& s, RawCamera const& cam, bool have_camera)
+bool near_root_only(RawSphere const& s, ptb_context const* ctx)
 {
-    if(s.reflection == 2 || !have_camera) {
+    if(s.reflection == 2 || (!ctx->have_camera && !ctx->have_sbcam)) {
         return false;
     }
-    double const dx = cam.pos[0] - s.px, dy = cam.pos[1] - s.py, dz = cam.pos[2] - s.pz;
-    double const dist = std::sqrt(dx * dx + dy * dy + dz * dz);
-    return dist > s.radius + 3.0 * std::fabs(cam.lens_radius) + 1e-9;
+    auto outside = [&](double const* pos, double slack) {
+        double const dx = pos[0] - s.px, dy = pos[1] - s.py, dz = pos[2] - s.pz;
+        return std::sqrt(dx * dx + dy * dy + dz * dz) > s.radius + slack + 1e-9;
+    };
+    bool ok = true;
+    if(ctx->have_camera) {
+        ok = ok && outside(ctx->h_camera.pos, 3.0 * std::fabs(ctx->h_camera.lens_radius));
+    }
+    if(ctx->have_sbcam) {
+        // rays start at position + push * unit direction, direction within the field of view: test the
+        // whole segment's end region conservatively through both end points and the push distance
+        double const* c = ctx->sb_cam8;
+        double const len = std::sqrt(c[3] * c[3] + c[4] * c[4] + c[5] * c[5]);
+        double const start[3] = { c[0] + c[7] * c[3] / len, c[1] + c[7] * c[4] / len, c[2] + c[7] * c[5] / len };
+        // the pushed origins lie within push * (half the image plane extent) of `start`:
+        // half width = fov * aspect / 2, half height = fov / 2 (sandbox/main.cpp:236-237,258-260); 20 % margin.
+        // The aspect ratio is only known once the image is set: assume a very wide image until then.
+        double const aspect = ctx->width > 0 ? static_cast<double>(ctx->width) / ctx->height : 4.0;
+        double const half = 0.5 * std::fabs(c[6]) * std::sqrt(aspect * aspect + 1.0);
+        ok = ok && outside(start, 1.2 * std::fabs(c[7]) * half);
+    }
+    return ok;
 }
 
 PackedScene pack_geometry(ptb_context* ctx)
@@ -193,7 +215,7 @@ PackedScene pack_geometry(ptb_context* ctx)
     bool uniform_k = true, any_big = false;
     for(int i = 0; i < n; ++i) {
         bool const big = s[i].radius > kBigRadius;
-        bool const near_only = near_root_only(s[i], ctx->h_camera, ctx->have_camera);
+        bool const near_only = near_root_only(s[i], ctx);
         if(big) {
             double const k = 1.0 / (2.0 * s[i].radius);
             if(!any_big) {
@@ -224,6 +246,26 @@ PackedScene pack_geometry(ptb_context* ctx)
     out.counts.big_y = static_cast<int>(big_near[1].size());
     out.counts.big_z = static_cast<int>(big_near[2].size());
     out.counts.uniform_k = any_big && uniform_k;
+    // index-in-key truncates t by < 2^-19 relative: allowed while 2e-6 * (scene extent) << epsilon = 1e-4.
+    // Extent = reach of the ordinary spheres and the cameras from the frame origin.
+    double extent = 0.0;
+    for(int i = 0; i < n; ++i) {
+        if(s[i].radius <= kBigRadius) {
+            double const x = s[i].px - sh[0], y = s[i].py - sh[1], z = s[i].pz - sh[2];
+            extent = std::max(extent, std::sqrt(x * x + y * y + z * z) + s[i].radius);
+        }
+    }
+    auto reach = [&](double const* q) {
+        double const x = q[0] - sh[0], y = q[1] - sh[1], z = q[2] - sh[2];
+        return std::sqrt(x * x + y * y + z * z);
+    };
+    if(ctx->have_camera) {
+        extent = std::max(extent, reach(ctx->h_camera.pos));
+    }
+    if(ctx->have_sbcam) {
+        extent = std::max(extent, reach(ctx->sb_cam8));
+    }
+    out.counts.embed_ok = extent <= 8.0;
     out.counts.fits_const = out.counts.small_near + out.counts.small_both <= kMaxConstSpheres &&
                             out.counts.big_near + out.counts.big_both <= kMaxConstSpheres;
     for(auto const& l : lists) {
@@ -306,6 +348,31 @@ void pack_camera(ptb_context* ctx)
     o.inv_w = ctx->width > 0 ? static_cast<float>(1.0 / ctx->width) : 0.0f;
     o.inv_h = ctx->height > 0 ? static_cast<float>(1.0 / ctx->height) : 0.0f;
     o.sub_len = ctx->ns > 0 ? static_cast<float>(1.0 / ctx->ns) : 0.0f;
+
+    // sandbox/main.cpp:235-237: cam.d normalised, cx = (w * fov / h, 0, 0), cy = norm(cx x d) * fov
+    SmallptCamF32& sbc = ctx->cs.sbcam;
+    sbc = SmallptCamF32{};
+    if(ctx->have_sbcam && ctx->width > 0) {
+        double const* c8 = ctx->sb_cam8;
+        double const len = std::sqrt(c8[3] * c8[3] + c8[4] * c8[4] + c8[5] * c8[5]);
+        double const d[3] = { c8[3] / len, c8[4] / len, c8[5] / len };
+        double const cxx = ctx->width * c8[6] / ctx->height;
+        double cy[3] = { 0.0 * d[2] - 0.0 * d[1], 0.0 * d[0] - cxx * d[2], cxx * d[1] - 0.0 * d[0] };
+        double const cyl = std::sqrt(cy[0] * cy[0] + cy[1] * cy[1] + cy[2] * cy[2]);
+        sbc.ox = static_cast<float>(c8[0] - sh[0]);
+        sbc.oy = static_cast<float>(c8[1] - sh[1]);
+        sbc.oz = static_cast<float>(c8[2] - sh[2]);
+        sbc.dx = static_cast<float>(d[0]);
+        sbc.dy = static_cast<float>(d[1]);
+        sbc.dz = static_cast<float>(d[2]);
+        sbc.cxx = static_cast<float>(cxx);
+        sbc.cyx = static_cast<float>(cy[0] / cyl * c8[6]);
+        sbc.cyy = static_cast<float>(cy[1] / cyl * c8[6]);
+        sbc.cyz = static_cast<float>(cy[2] / cyl * c8[6]);
+        sbc.push = static_cast<float>(c8[7]);
+        sbc.inv_w = static_cast<float>(1.0 / ctx->width);
+        sbc.inv_h = static_cast<float>(1.0 / ctx->height);
+    }
 }
 
 // (Re)build everything derived from (spheres, camera, image geometry) and push the
@@ -391,7 +458,7 @@ GeoLists geo_lists(ptb_context* ctx)
     return g;
 }
 
-int require_ready(ptb_context* ctx, bool need_image)
+int require_ready(ptb_context* ctx, bool need_image, bool smallpt = false, bool any_camera = false)
 {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
@@ -399,8 +466,8 @@ int require_ready(ptb_context* ctx, bool need_image)
     if(!ctx->have_scene) {
         return fail(ctx, PTB_ERR_STATE, "no scene: call ptb_upload_scene first");
     }
-    if(!ctx->have_camera) {
-        return fail(ctx, PTB_ERR_STATE, "no camera: call ptb_set_camera first");
+    if(any_camera ? (!ctx->have_camera && !ctx->have_sbcam) : (smallpt ? !ctx->have_sbcam : !ctx->have_camera)) {
+        return fail(ctx, PTB_ERR_STATE, smallpt ? "no camera: call ptb_set_smallpt_camera first" : "no camera: call ptb_set_camera first");
     }
     if(need_image && (ctx->width <= 0 || active_accum(ctx) == nullptr)) {
         return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
@@ -489,6 +556,7 @@ void ptb_destroy(ptb_context* ctx)
     }
     cudaFree(ctx->d_spheres);
     cudaFree(ctx->d_camera);
+    cudaFree(ctx->d_sbcam8);
     cudaFree(ctx->d_small);
     cudaFree(ctx->d_big);
     cudaFree(ctx->d_order);
@@ -599,6 +667,28 @@ int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
     return PTB_OK;
 }
 
+int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(cam8 == nullptr || (cam8[3] == 0.0 && cam8[4] == 0.0 && cam8[5] == 0.0)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_smallpt_camera: need position(3), non-zero direction(3), fov factor, push");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::memcpy(ctx->sb_cam8, cam8, sizeof(ctx->sb_cam8));
+    if(ctx->d_sbcam8 == nullptr) {
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_sbcam8, sizeof(ctx->sb_cam8)));
+    }
+    PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sbcam8, ctx->sb_cam8, sizeof(ctx->sb_cam8), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_sbcam = true;
+    if(ctx->have_scene) {
+        return rebuild_device_scene(ctx);
+    }
+    return PTB_OK;
+}
+
 int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
 {
     if(ctx == nullptr) {
@@ -638,9 +728,13 @@ int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
         ctx->ext_accum = nullptr;
         ctx->ext_accum_bytes = 0;
     }
-    if(ctx->have_camera) {
-        pack_camera(ctx);
+    if(ctx->have_scene && ctx->have_sbcam) {
+        int const rc = rebuild_device_scene(ctx); // near-root-only classification depends on the aspect ratio
+        if(rc != PTB_OK) {
+            return rc;
+        }
     }
+    pack_camera(ctx);
     return ptb_clear(ctx);
 }
 
@@ -667,15 +761,24 @@ int ptb_clear(ptb_context* ctx)
 
 int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t samples_per_subpixel, uint32_t flags)
 {
-    int rc = require_ready(ctx, true);
-    if(rc != PTB_OK) {
-        return rc;
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
     }
     uint32_t const variant = flags & PTB_VARIANT_MASK;
     uint32_t const precision = flags & PTB_PRECISION_MASK;
-    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK)) != 0 || variant > PTB_VARIANT_WAVEFRONT ||
-       (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64)) {
+    uint32_t const integrator = flags & PTB_INTEGRATOR_MASK;
+    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK)) != 0 || variant > PTB_VARIANT_WAVEFRONT ||
+       (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) ||
+       (integrator != PTB_INTEGRATOR_PT && integrator != PTB_INTEGRATOR_SMALLPT)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
+    }
+    bool const smallpt = integrator == PTB_INTEGRATOR_SMALLPT;
+    int rc = require_ready(ctx, true, smallpt);
+    if(rc != PTB_OK) {
+        return rc;
+    }
+    if(smallpt && (variant == PTB_VARIANT_WAVEFRONT || ctx->ns != 2)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: the smallpt integrator is megakernel-only and uses 2x2 sub-pixels (sandbox/main.cpp:248-249)");
     }
     if(variant == PTB_VARIANT_WAVEFRONT && precision == PTB_PRECISION_FP64) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: the wavefront variant exists in FP32 only");
@@ -705,9 +808,16 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
             PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum64, 0, ctx->nslots * 4 * sizeof(double), st));
         }
         ctx->accum64_used = true;
-        PTB_CUDA(ctx, launch_render_f64(key, first_sample, samples_per_subpixel, static_cast<uint32_t>(ctx->width),
-                                        static_cast<uint32_t>(ctx->height), static_cast<uint32_t>(ctx->ns),
-                                        ctx->d_spheres, ctx->n, ctx->d_camera, ctx->d_accum64, ctx->d_counters, st));
+        if(smallpt) {
+            PTB_CUDA(ctx, launch_smallpt_render_f64(key, first_sample, samples_per_subpixel, static_cast<uint32_t>(ctx->width),
+                                                    static_cast<uint32_t>(ctx->height), ctx->d_spheres, ctx->n, ctx->d_sbcam8,
+                                                    ctx->d_accum64, ctx->d_counters, st));
+        }
+        else {
+            PTB_CUDA(ctx, launch_render_f64(key, first_sample, samples_per_subpixel, static_cast<uint32_t>(ctx->width),
+                                            static_cast<uint32_t>(ctx->height), static_cast<uint32_t>(ctx->ns),
+                                            ctx->d_spheres, ctx->n, ctx->d_camera, ctx->d_accum64, ctx->d_counters, st));
+        }
         launches = 1;
     }
     else {
@@ -757,7 +867,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
             PTB_CUDA(ctx, launch_wavefront(buf, p, ctx->counts, ctx->sm_count, st, &launches));
         }
         else {
-            PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches));
+            PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches, smallpt));
         }
     }
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -773,7 +883,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
 
 static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
 {
-    int rc = require_ready(ctx, true);
+    int rc = require_ready(ctx, true, false, true);
     if(rc != PTB_OK) {
         return rc;
     }
@@ -810,7 +920,7 @@ int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out)
 
 int ptb_resolve_device(ptb_context* ctx, void** device_rgb)
 {
-    int rc = require_ready(ctx, true);
+    int rc = require_ready(ctx, true, false, true);
     if(rc != PTB_OK) {
         return rc;
     }
@@ -945,7 +1055,8 @@ int ptb_scene_layout(ptb_context* ctx, int32_t out[10])
     }
     SceneCounts const& c = ctx->counts;
     int32_t const v[10] = { c.small_near, c.small_both, c.big_near, c.big_both, c.big_x, c.big_y, c.big_z,
-                            c.uniform_k ? 1 : 0, c.fits_const ? 1 : 0, megakernel_has_specialisation(c) ? 1 : 0 };
+                            (c.uniform_k ? 1 : 0) | (c.embed_ok ? 2 : 0), c.fits_const ? 1 : 0,
+                            megakernel_has_specialisation(c) ? 1 : 0 };
     std::memcpy(out, v, sizeof(v));
     return PTB_OK;
 }
@@ -954,12 +1065,19 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
                       uint32_t const* sy, uint32_t const* sample, size_t count, uint32_t flags, int32_t* primary_hit_out,
                       double* radiance_out, double* ray_out, uint32_t* draws_out)
 {
-    int rc = require_ready(ctx, false);
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    bool const smallpt = (flags & PTB_INTEGRATOR_MASK) == PTB_INTEGRATOR_SMALLPT;
+    int rc = require_ready(ctx, false, smallpt);
     if(rc != PTB_OK) {
         return rc;
     }
     if(ctx->width <= 0) {
         return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(smallpt && ctx->ns != 2) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: the smallpt integrator uses 2x2 sub-pixels");
     }
     if(x == nullptr || y == nullptr || sx == nullptr || sy == nullptr || sample == nullptr || primary_hit_out == nullptr ||
        radiance_out == nullptr || count > (1u << 30)) {
@@ -1026,11 +1144,16 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
     q.ray = d_ray;
     q.draws = d_draws;
     if(precision == PTB_PRECISION_FP64) {
-        PTB_CUDA_T(launch_probe_f64(q, ctx->d_spheres, ctx->n, ctx->d_camera, st));
+        if(smallpt) {
+            PTB_CUDA_T(launch_smallpt_probe_f64(q, ctx->d_spheres, ctx->n, ctx->d_sbcam8, st));
+        }
+        else {
+            PTB_CUDA_T(launch_probe_f64(q, ctx->d_spheres, ctx->n, ctx->d_camera, st));
+        }
     }
     else {
         PTB_CUDA_T(upload_const_scene(ctx->cs, st));
-        PTB_CUDA_T(launch_probe_f32(q, ctx->counts, shade_planes(ctx), geo_lists(ctx), st));
+        PTB_CUDA_T(launch_probe_f32(q, ctx->counts, shade_planes(ctx), geo_lists(ctx), st, smallpt));
     }
     ctx->stats.kernel_launches += 1;
     PTB_CUDA_T(cudaMemcpyAsync(primary_hit_out, d_hit, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

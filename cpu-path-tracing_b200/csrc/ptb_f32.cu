@@ -23,6 +23,7 @@
 //     state, progressive by construction.
 #include "ptb_kernels.h"
 #include "ptb_path_f32.cuh"
+#include "ptb_smallpt_f32.cuh"
 
 namespace ptb {
 
@@ -63,11 +64,63 @@ struct WarpRing
 };
 constexpr uint32_t kVoidSlot = 0xFFFFFFFFu;
 
-template<class Shape, bool kSmemShade>
+// ---- integrator policies: what differs between the two programs of the reference ---------------------------
+// src/main.cpp: thin-lens camera, iterative radiance (ptb_path_f32.cuh).  Ring word b.y carries `len`
+// (the origin's z is the camera's: the lens offset has no z component).
+struct IntegratorPt
+{
+    static constexpr bool kSplit = false;
+    __device__ static __forceinline__ void generate(PathF32& g, uint32_t x, uint32_t y, uint32_t sx, uint32_t sy)
+    {
+        gen_primary(g, c_scene.cam, x, y, sx, sy);
+    }
+    __device__ static __forceinline__ float ring_word(PathF32 const& g)
+    {
+        return g.len;
+    }
+    __device__ static __forceinline__ void unpack(PathF32& p, float word)
+    {
+        p.len = word;
+        p.oz = c_scene.cam.pz;
+    }
+    __device__ static __forceinline__ bool bounce(PathF32& p, bool hit, float t, int id, ShadePlanes const& sp,
+                                                  BounceCounters& cnt, SplitStack&)
+    {
+        return shade_bounce<true>(p, hit, t, id, sp, cnt);
+    }
+};
+// sandbox/main.cpp (stand-alone smallpt): pinhole tent-filter camera, splitting glass (ptb_smallpt_f32.cuh).
+// Directions are always unit (len == 1), so ring word b.y carries the origin's z instead.
+struct IntegratorSmallpt
+{
+    static constexpr bool kSplit = true;
+    __device__ static __forceinline__ void generate(PathF32& g, uint32_t x, uint32_t y, uint32_t sx, uint32_t sy)
+    {
+        gen_smallpt(g, c_scene.sbcam, x, y, sx, sy);
+    }
+    __device__ static __forceinline__ float ring_word(PathF32 const& g)
+    {
+        return g.oz;
+    }
+    __device__ static __forceinline__ void unpack(PathF32& p, float word)
+    {
+        p.len = 1.0f;
+        p.oz = word;
+    }
+    __device__ static __forceinline__ bool bounce(PathF32& p, bool hit, float t, int id, ShadePlanes const& sp,
+                                                  BounceCounters& cnt, SplitStack& st)
+    {
+        return bounce_smallpt<true>(p, hit, t, id, sp, cnt, st);
+    }
+};
+
+template<class Shape, bool kSmemShade, class Integ>
 __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 const prm)
 {
     __shared__ float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
     __shared__ WarpRing s_ring[kMegaThreads / 32];
+    __shared__ float s_split[Integ::kSplit ? 2 * kSplitFields * kMegaThreads : 1];
+    SplitStack split{ s_split, kMegaThreads, 0 };
     ShadePlanes sp = prm.shade;
     if constexpr(kSmemShade) {
         for(int i = threadIdx.x; i < prm.n_total; i += kMegaThreads) {
@@ -129,15 +182,15 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
             }
             if(!exhausted) {
                 PathF32 g;
-                g.dx = g.dy = g.dz = g.ox = g.oy = g.len = 0.0f;
+                g.dx = g.dy = g.dz = g.ox = g.oy = g.oz = g.len = 0.0f;
                 g.rng.state = g.rng.inc = 0u;
                 if(gen_slot != kVoidSlot) {
                     g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
-                    gen_primary(g, c_scene.cam, gen_x, gen_y, gen_sx, gen_sy);
+                    Integ::generate(g, gen_x, gen_y, gen_sx, gen_sy);
                 }
                 uint32_t const w = (ring_head + lane) & (kRingSize - 1);
                 ring.a[w] = make_float4(g.ox, g.oy, g.dx, g.dy);
-                ring.b[w] = make_float4(g.dz, g.len, __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc));
+                ring.b[w] = make_float4(g.dz, Integ::ring_word(g), __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc));
                 ring.slot[w] = gen_slot;
                 ring_head = (ring_head + 32u) & (kRingSize - 1);
                 ring_count += 32u;
@@ -158,16 +211,16 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                 if(slot != kVoidSlot) {
                     p.ox = ea.x;
                     p.oy = ea.y;
-                    p.oz = c_scene.cam.pz;
                     p.dx = ea.z;
                     p.dy = ea.w;
                     p.dz = eb.x;
-                    p.len = eb.y;
+                    Integ::unpack(p, eb.y);
                     p.rng.state = __float_as_uint(eb.z);
                     p.rng.inc = __float_as_uint(eb.w);
                     p.tr = p.tg = p.tb = 1.0f;
                     p.er = p.eg = p.eb = 0.0f;
                     p.depth = 0;
+                    p.last = -1;
                     alive = true;
                 }
             }
@@ -191,7 +244,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
             int id;
             bool const hit = closest_hit<Shape>(c_scene, prm.geo, p, r, t, id);
             cnt.rays++;
-            alive = shade_bounce<true>(p, hit, t, id, sp, cnt);
+            alive = Integ::bounce(p, hit, t, id, sp, cnt, split);
             if(!alive) {
                 red_add_v4(prm.accum + slot, p.er, p.eg, p.eb, 1.0f);
             }
@@ -214,23 +267,24 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
 // (small near-only, small both-roots, big near-only, big both-roots) list lengths with a fully
 // unrolled kernel.  Everything else runs the generic run-time-count variant.
 #define PTB_MEGA_SPECIALISATIONS(X) \
-    X(2, 1, 5, 0, 2, 2, 1, true)  /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball | glass ball | 5 R=1e6 walls on the frame axes */ \
-    X(3, 1, 1, 0, 0, 1, 0, true)  /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100, on the y axis)                       */ \
-    X(2, 2, 1, 0, 0, 1, 0, true)  /* depth-of-field scene (BASELINE config 4): two glass spheres                                             */ \
-    X(2, 1, 5, 0, 0, 0, 0, false) /* box scenes in a frame where the walls are not axis spheres                                             */ \
-    X(0, 3, 0, 5, 0, 0, 0, false) /* box scenes with the camera inside every sphere's reach: all both-roots                                 */ \
-    X(1, 0, 0, 0, 0, 0, 0, false) \
-    X(0, 1, 0, 0, 0, 0, 0, false) \
-    X(8, 0, 0, 0, 0, 0, 0, false)
+    X(2, 1, 5, 0, 2, 2, 1, true, true)   /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball | glass ball | 5 R=1e6 walls on the frame axes */ \
+    X(3, 1, 1, 0, 0, 1, 0, true, true)   /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100, on the y axis)                       */ \
+    X(2, 2, 1, 0, 0, 1, 0, true, true)   /* depth-of-field scene (BASELINE config 4): two glass spheres                                             */ \
+    X(2, 1, 5, 0, 0, 0, 0, false, true)  /* box scenes in a frame where the walls are not axis spheres                                             */ \
+    X(0, 3, 0, 5, 0, 0, 0, false, true)  /* box scenes with the camera inside every sphere's reach: all both-roots                                 */ \
+    X(3, 1, 0, 6, 0, 0, 0, true, false)  /* sandbox/main.cpp: 2 mirrors + light | glass | six R=1e5 walls seen from INSIDE; ~300 units across     */ \
+    X(1, 0, 0, 0, 0, 0, 0, false, true) \
+    X(0, 1, 0, 0, 0, 0, 0, false, true) \
+    X(8, 0, 0, 0, 0, 0, 0, false, true)
 
-#define PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk) \
+#define PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) \
     ((c).small_near == (a) && (c).small_both == (b) && (c).big_near == (cc) && (c).big_both == (d) && (c).big_x == (bx) && \
-     (c).big_y == (by) && (c).big_z == (bz) && (c).uniform_k == (uk) && (c).fits_const)
+     (c).big_y == (by) && (c).big_z == (bz) && (c).uniform_k == (uk) && (c).embed_ok == (em) && (c).fits_const)
 
 bool megakernel_has_specialisation(SceneCounts const& c)
 {
-#define X(a, b, cc, d, bx, by, bz, uk) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk)) { \
+#define X(a, b, cc, d, bx, by, bz, uk, em) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em)) { \
         return true; \
     }
     PTB_MEGA_SPECIALISATIONS(X)
@@ -238,11 +292,11 @@ bool megakernel_has_specialisation(SceneCounts const& c)
     return false;
 }
 
-template<class Shape, bool kSmem>
+template<class Shape, bool kSmem, class Integ>
 static cudaError_t launch_one(RenderParamsF32 const& p, int sm_count, cudaStream_t stream)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel<Shape, kSmem>, kMegaThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel<Shape, kSmem, Integ>, kMegaThreads, 0);
     if(e != cudaSuccess) {
         return e;
     }
@@ -258,12 +312,28 @@ static cudaError_t launch_one(RenderParamsF32 const& p, int sm_count, cudaStream
     if(blocks < 1) {
         blocks = 1;
     }
-    mega_kernel<Shape, kSmem><<<static_cast<unsigned>(blocks), kMegaThreads, 0, stream>>>(p);
+    mega_kernel<Shape, kSmem, Integ><<<static_cast<unsigned>(blocks), kMegaThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
+template<class Integ>
+static cudaError_t launch_mega_integrator(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream)
+{
+    bool const smem = p.n_total <= kSmemShadeSpheres;
+#define X(a, b, cc, d, bx, by, bz, uk, em) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) && smem) { \
+        return launch_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, true, Integ>(p, sm_count, stream); \
+    }
+    PTB_MEGA_SPECIALISATIONS(X)
+#undef X
+    if(smem) {
+        return launch_one<GenericShape, true, Integ>(p, sm_count, stream);
+    }
+    return launch_one<GenericShape, false, Integ>(p, sm_count, stream);
+}
+
 cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
-                              int* launches)
+                              int* launches, bool smallpt)
 {
     cudaError_t e = cudaMemsetAsync(&p.counters->tile_cursor, 0, sizeof(unsigned long long), stream);
     if(e != cudaSuccess) {
@@ -272,17 +342,8 @@ cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, in
     if(launches != nullptr) {
         *launches += 1;
     }
-    bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d, bx, by, bz, uk) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk) && smem) { \
-        return launch_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk)>, true>(p, sm_count, stream); \
-    }
-    PTB_MEGA_SPECIALISATIONS(X)
-#undef X
-    if(smem) {
-        return launch_one<GenericShape, true>(p, sm_count, stream);
-    }
-    return launch_one<GenericShape, false>(p, sm_count, stream);
+    return smallpt ? launch_mega_integrator<IntegratorSmallpt>(p, c, sm_count, stream)
+                   : launch_mega_integrator<IntegratorPt>(p, c, sm_count, stream);
 }
 
 } // namespace ptb
@@ -294,9 +355,11 @@ namespace ptb {
 // ---- FP32 probe ---------------------------------------------------------------------------------
 // One thread per requested sample; same device functions AND the same (n_small, n_big)
 // specialisation as the megakernel, so the probe traces what the renderer traces.
-template<class Shape>
-__global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoLists const geo)
+template<class Shape, class Integ>
+__global__ void __launch_bounds__(kMegaThreads) probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoLists const geo)
 {
+    __shared__ float s_split[Integ::kSplit ? 2 * kSplitFields * kMegaThreads : 1];
+    SplitStack split{ s_split, kMegaThreads, 0 };
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= q.count) {
         return;
@@ -305,8 +368,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
     uint32_t const slot = ((y * q.width + x) * q.ns + sy) * q.ns + sx;
     PathF32 p;
     p.rng = rng_open(q.key, slot, q.sample[i]);
-    p.oz = c_scene.cam.pz;
-    gen_primary(p, c_scene.cam, x, y, sx, sy);
+    Integ::generate(p, x, y, sx, sy);
     if(q.ray != nullptr) {
         q.ray[6 * i + 0] = p.ox;
         q.ray[6 * i + 1] = p.oy;
@@ -330,7 +392,7 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
         float t;
         int id;
         bool const hit = closest_hit<Shape>(c_scene, geo, p, r, t, id);
-        alive = shade_bounce<true>(p, hit, t, id, sp, cnt);
+        alive = Integ::bounce(p, hit, t, id, sp, cnt, split);
     }
     q.radiance[3 * i + 0] = p.er;
     q.radiance[3 * i + 1] = p.eg;
@@ -340,23 +402,31 @@ __global__ void probe_f32_kernel(ProbeParams const q, ShadePlanes const sp, GeoL
     }
 }
 
-cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade, GeoLists const& geo,
-                             cudaStream_t stream)
+template<class Integ>
+static cudaError_t launch_probe_integrator(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade,
+                                           GeoLists const& geo, cudaStream_t stream)
 {
-    if(p.count == 0) {
-        return cudaSuccess;
-    }
-    unsigned const threads = 128;
+    unsigned const threads = kMegaThreads;
     unsigned const blocks = (p.count + threads - 1) / threads;
-#define X(a, b, cc, d, bx, by, bz, uk) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk)) { \
-        probe_f32_kernel<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk)>><<<blocks, threads, 0, stream>>>(p, shade, geo); \
+#define X(a, b, cc, d, bx, by, bz, uk, em) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em)) { \
+        probe_f32_kernel<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, Integ><<<blocks, threads, 0, stream>>>(p, shade, geo); \
         return cudaGetLastError(); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X
-    probe_f32_kernel<GenericShape><<<blocks, threads, 0, stream>>>(p, shade, geo);
+    probe_f32_kernel<GenericShape, Integ><<<blocks, threads, 0, stream>>>(p, shade, geo);
     return cudaGetLastError();
+}
+
+cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade, GeoLists const& geo,
+                             cudaStream_t stream, bool smallpt)
+{
+    if(p.count == 0) {
+        return cudaSuccess;
+    }
+    return smallpt ? launch_probe_integrator<IntegratorSmallpt>(p, c, shade, geo, stream)
+                   : launch_probe_integrator<IntegratorPt>(p, c, shade, geo, stream);
 }
 
 // ---- raw draws of the stream (device side), for tests/test_rng.py ----------------------------------

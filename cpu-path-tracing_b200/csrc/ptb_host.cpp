@@ -7,6 +7,31 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
+
+namespace {
+template<class ToInt>
+int write_ppm_with(char const* path, double const* rgb, int width, int height, ToInt to_int)
+{
+    if(path == nullptr || rgb == nullptr || width <= 0 || height <= 0) {
+        return PTB_ERR_ARGUMENT;
+    }
+    std::FILE* f = std::fopen(path, "wb");
+    if(f == nullptr) {
+        return PTB_ERR_IO;
+    }
+    std::string buf;
+    buf.reserve(static_cast<size_t>(width) * static_cast<size_t>(height) * 12 + 32);
+    buf += "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
+    size_t const n = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
+    for(size_t i = 0; i < n; ++i) {
+        buf += std::to_string(to_int(rgb[i]));
+        buf += ' ';
+    }
+    bool const ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    return (std::fclose(f) == 0 && ok) ? PTB_OK : PTB_ERR_IO;
+}
+} // namespace
 
 extern "C" {
 
@@ -69,27 +94,36 @@ int ptb_builtin_scene(char const* name, int width, int height, void* spheres_out
     return PTB_OK;
 }
 
+int ptb_builtin_smallpt_scene(void* spheres_out, size_t capacity, size_t* count_out, double* cam8_out)
+{
+    std::vector<pt::sphere> const spheres = pt::smallpt_scene();
+    if(count_out != nullptr) {
+        *count_out = spheres.size();
+    }
+    if(cam8_out != nullptr) {
+        pt::smallpt_camera const cam{};
+        std::memcpy(cam8_out, static_cast<void const*>(&cam), sizeof(cam));
+    }
+    if(spheres_out != nullptr) {
+        if(capacity < spheres.size()) {
+            return PTB_ERR_ARGUMENT;
+        }
+        std::memcpy(spheres_out, static_cast<void const*>(spheres.data()), sizeof(pt::sphere) * spheres.size());
+    }
+    return PTB_OK;
+}
+
+// sandbox/main.cpp:271-275: same P3 layout, toInt rounding
+int ptb_write_ppm_smallpt(char const* path, double const* rgb, int width, int height)
+{
+    return write_ppm_with(path, rgb, width, height, [](double v) { return pt::smallpt_to_int(v); });
+}
+
 // Same bytes as the writer of /root/reference/src/main.cpp:240-247: header
 // "P3\n{w} {h}\n255\n", then "{r} {g} {b} " per pixel, no newlines.
 int ptb_write_ppm(char const* path, double const* rgb, int width, int height)
 {
-    if(path == nullptr || rgb == nullptr || width <= 0 || height <= 0) {
-        return PTB_ERR_ARGUMENT;
-    }
-    std::FILE* f = std::fopen(path, "wb");
-    if(f == nullptr) {
-        return PTB_ERR_IO;
-    }
-    std::string buf;
-    buf.reserve(static_cast<size_t>(width) * static_cast<size_t>(height) * 12 + 32);
-    buf += "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
-    size_t const n = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
-    for(size_t i = 0; i < n; ++i) {
-        buf += std::to_string(pt::color_to_int(rgb[i]));
-        buf += ' ';
-    }
-    bool const ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
-    return (std::fclose(f) == 0 && ok) ? PTB_OK : PTB_ERR_IO;
+    return write_ppm_with(path, rgb, width, height, [](double v) { return pt::color_to_int(v); });
 }
 
 } // extern "C"

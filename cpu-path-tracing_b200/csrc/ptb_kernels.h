@@ -50,12 +50,13 @@ struct SceneCounts
     bool fits_const = true; // both classes fit the __constant__ lists
     int big_x = 0, big_y = 0, big_z = 0; // prefix of the near-only big list: centres on a frame axis
     bool uniform_k = false;              // every big sphere has the same radius
+    bool embed_ok = true;                // scene small enough against epsilon for index-in-key (ptb_path_f32.cuh)
 };
 // True when a fully unrolled kernel exists for these list lengths.
 bool megakernel_has_specialisation(SceneCounts const& c);
 // Launch the persistent megakernel: grid = SM count * resident blocks.
 cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
-                              int* launches);
+                              int* launches, bool smallpt);
 
 // ---- wavefront / material-sorted variant (ptb_wavefront.cuh) ------------------------------------------
 struct WavefrontCounters
@@ -97,7 +98,14 @@ struct ProbeParams
     uint32_t* draws;  // [count] or nullptr
 };
 cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade, GeoLists const& geo,
-                             cudaStream_t stream);
+                             cudaStream_t stream, bool smallpt);
+
+// ---- stand-alone smallpt fork, FP64 parity (ptb_smallpt_f64.cu); cam8 is device memory -----------------------------
+cudaError_t launch_smallpt_probe_f64(ProbeParams const& p, RawSphere const* spheres, int n, double const* cam8,
+                                     cudaStream_t stream);
+cudaError_t launch_smallpt_render_f64(uint64_t key, uint32_t first_sample, uint32_t samples, uint32_t width, uint32_t height,
+                                      RawSphere const* spheres, int n, double const* cam8, double* accum64,
+                                      DeviceCounters* counters, cudaStream_t stream);
 
 // ---- FP64 parity path (reference operation order, no FMA contraction) ----------------------------------
 cudaError_t launch_probe_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam,

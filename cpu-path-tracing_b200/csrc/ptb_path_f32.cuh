@@ -19,7 +19,11 @@
 
 namespace ptb {
 
+#ifdef PTB_EPS
+constexpr float kEpsilon = PTB_EPS;
+#else
 constexpr float kEpsilon = 1e-4f;      // constants.hpp:7
+#endif
 constexpr int kDepthLimit = 100;       // constants.hpp:10
 constexpr int kRouletteThreshold = 4;  // main.cpp:106
 constexpr uint32_t kNoHitBits = 0x7F800000u; // +inf: also what "t < inf" (main.cpp:41) becomes
@@ -66,6 +70,7 @@ struct PathF32
     float er, eg, eb; // accumulated_emission   (main.cpp:107)
     Rng rng;
     int depth;
+    int last; // list position of the sphere this ray starts on, -1 for a camera ray (robust shapes only)
 };
 
 // slot -> (x, y, sx, sy) in reference loop coordinates; slot = ((y*W+x)*ns+sy)*ns+sx
@@ -131,6 +136,7 @@ __device__ __forceinline__ void gen_primary(PathF32& p, CameraF32 const& cam, ui
     p.tr = p.tg = p.tb = 1.0f;
     p.er = p.eg = p.eb = 0.0f;
     p.depth = 0;
+    p.last = -1;
 }
 
 // Per-ray invariants of the sphere tests.
@@ -163,8 +169,13 @@ __device__ __forceinline__ RayTerms ray_terms(PathF32 const& p, float k_uniform 
 // ABOVE +inf, so a single unsigned min does "root < eps -> try the far root -> reject"
 // (sphere.cpp:21-27).  kBoth = false keeps the near root only (opaque sphere seen from
 // outside: the far root can never be the answer).
-template<bool kBoth>
-__device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& p, RayTerms const& r)
+// kRobust (scenes that are large against epsilon, and every run-time-count scene): a ray that starts ON
+// sphere `self` knows one root of that sphere is 0 -- the point it stands on -- so the other one is
+// 2*nb exactly; taking it from there instead of from nb +- sqrt(nb^2 - c) with c ~ 0 removes the
+// binary32 failure where a ray refracted OUT of a glass ball re-hits it from inside a few 1e-4 further
+// on, is totally reflected and then circles inside for ~1000 bounces (seen on the sandbox scene).
+template<bool kBoth, bool kRobust = false>
+__device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& p, RayTerms const& r, bool self = false)
 {
     float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz; // c - o = -oc
     float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));       // -half_b
@@ -173,13 +184,18 @@ __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& 
     float const sq = disc_sqrt(disc);
     float const h = nb - r.eps;
     float const tn = h - sq;
+    uint32_t key;
     if constexpr(kBoth) {
         float const tf = h + sq;
-        return min(__float_as_uint(tn), __float_as_uint(tf));
+        key = min(__float_as_uint(tn), __float_as_uint(tf));
     }
     else {
-        return __float_as_uint(tn);
+        key = __float_as_uint(tn);
     }
+    if constexpr(kRobust) {
+        key = self ? __float_as_uint(nb + h) : key; // 2*nb - eps
+    }
+    return key;
 }
 
 // Big-sphere form.  With m = sqrt(disc) + |hb| (no cancellation, m > 0) the two roots are
@@ -187,8 +203,8 @@ __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& 
 // which is the numerically stable pairing for EITHER sign of hb: the earlier c/(sqrt - hb)
 // is only safe for hb <= 0; moving away from a sphere (hb > 0) it divides by a difference
 // that rounding can turn into a tiny POSITIVE number, i.e. a spurious hit ~1e7 away.
-template<bool kBoth>
-__device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, RayTerms const& r)
+template<bool kBoth, bool kRobust = false>
+__device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, RayTerms const& r, bool self = false)
 {
     float const hb = fmaf(p.dx, b.gx, fmaf(p.dy, b.gy, fmaf(p.dz, b.gz, b.k * r.od)));           // half_b / 2R
     float const cp = fmaf(r.o2x, b.gx, fmaf(r.o2y, b.gy, fmaf(r.o2z, b.gz, fmaf(b.k, r.oo, b.K)))); // c / 2R
@@ -197,14 +213,20 @@ __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, R
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u; // sign bit set when hb >= 0 (sigma = -1)
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
     float const t1 = fmaf(cs, fast_rcp(m), -r.eps);
+    uint32_t key;
     if constexpr(kBoth) {
         float const ms = __uint_as_float(__float_as_uint(m) ^ flip);
         float const t2 = fmaf(ms, b.two_r, -r.eps);
-        return min(__float_as_uint(t1), __float_as_uint(t2));
+        key = min(__float_as_uint(t1), __float_as_uint(t2));
     }
     else {
-        return __float_as_uint(t1);
+        key = __float_as_uint(t1);
     }
+    if constexpr(kRobust) {
+        // standing on the sphere: roots are 0 and -2 hb / k
+        key = self ? __float_as_uint(fmaf(-2.0f * hb, b.two_r, -r.eps)) : key;
+    }
+    return key;
 }
 
 // Near-only big sphere whose centre lies ON a coordinate axis of the shifted frame (the host
@@ -230,9 +252,15 @@ __device__ __forceinline__ uint32_t key_big_axis(BigGeo const& b, PathF32 const&
 // Compile-time description of a scene's geometry lists; SN < 0 = run-time counts.
 //   SN small near-only, SB small both-roots, BN big near-only (of which the first BX / BY / BZ
 //   are x- / y- / z-axis spheres), BB big both-roots, UK = big spheres share one radius.
-template<int SN, int SB, int BN, int BB, int BX = 0, int BY = 0, int BZ = 0, bool UK = false>
+//   EM = the list position may ride in the low mantissa bits of the hit key (see closest_hit);
+//   only when the scene is small against epsilon: the 2^-19 relative truncation of t moves the
+//   hit point by up to 2e-6 * t, which must stay far below epsilon = 1e-4 (a refracted ray
+//   leaving a glass sphere re-hits it from inside otherwise -- seen on the sandbox scene, whose
+//   extent is ~300 units).
+template<int SN, int SB, int BN, int BB, int BX = 0, int BY = 0, int BZ = 0, bool UK = false, bool EM = true>
 struct SceneShape
 {
+    static constexpr bool embed = EM;
     static constexpr int small_near = SN, small_both = SB, big_near = BN, big_both = BB;
     static constexpr int big_x = BX, big_y = BY, big_z = BZ;
     static constexpr bool uniform_k = UK;
@@ -257,14 +285,24 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
     int id = -1;
     if constexpr(!Shape::generic) {
         static_assert(Shape::total <= (1 << kIdBits), "list position does not fit the key");
-        constexpr uint32_t keep = ~((1u << kIdBits) - 1u);
+        constexpr uint32_t keep = Shape::embed ? ~((1u << kIdBits) - 1u) : 0xFFFFFFFFu;
         constexpr int NS = Shape::small_near + Shape::small_both;
         constexpr int NB = Shape::big_near + Shape::big_both;
+        auto const take = [&](uint32_t k, int pos) {
+            if constexpr(Shape::embed) {
+                best = min(best, (k & keep) | static_cast<uint32_t>(pos));
+            }
+            else if(k < best) { // full-precision key: compare and select (two more half-rate ops per sphere)
+                best = k;
+                id = pos;
+            }
+        };
+        constexpr bool kRobust = !Shape::embed;
 #pragma unroll
         for(int i = 0; i < NS; ++i) {
-            uint32_t const k = i < Shape::small_near ? key_small<false>(cs.small_geo[i], p, r)
-                                                     : key_small<true>(cs.small_geo[i], p, r);
-            best = min(best, (k & keep) | static_cast<uint32_t>(i));
+            uint32_t const k = i < Shape::small_near ? key_small<false, kRobust>(cs.small_geo[i], p, r, p.last == i)
+                                                     : key_small<true, kRobust>(cs.small_geo[i], p, r, p.last == i);
+            take(k, i);
         }
 #pragma unroll
         for(int i = 0; i < NB; ++i) {
@@ -279,43 +317,45 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
                 k = key_big_axis<2, Shape::uniform_k>(cs.big_geo[i], p, r);
             }
             else if(i < Shape::big_near) {
-                k = key_big<false>(cs.big_geo[i], p, r);
+                k = key_big<false, kRobust>(cs.big_geo[i], p, r, p.last == NS + i);
             }
             else {
-                k = key_big<true>(cs.big_geo[i], p, r);
+                k = key_big<true, kRobust>(cs.big_geo[i], p, r, p.last == NS + i);
             }
-            best = min(best, (k & keep) | static_cast<uint32_t>(NS + i));
+            take(k, NS + i);
         }
-        id = static_cast<int>(best & ~keep);
-        best &= keep;
+        if constexpr(Shape::embed) {
+            id = static_cast<int>(best & ~keep);
+            best &= keep;
+        }
     }
     else {
         int const nsn = cs.n_small_near, ns = cs.n_small;
         int const nbn = cs.n_big_near, nb = cs.n_big;
 #pragma unroll 4
         for(int i = 0; i < nsn; ++i) {
-            uint32_t const k = key_small<false>(gl.small_geo[i], p, r);
+            uint32_t const k = key_small<false, true>(gl.small_geo[i], p, r, p.last == i);
             if(k < best) {
                 best = k;
                 id = i;
             }
         }
         for(int i = nsn; i < ns; ++i) {
-            uint32_t const k = key_small<true>(gl.small_geo[i], p, r);
+            uint32_t const k = key_small<true, true>(gl.small_geo[i], p, r, p.last == i);
             if(k < best) {
                 best = k;
                 id = i;
             }
         }
         for(int i = 0; i < nbn; ++i) {
-            uint32_t const k = key_big<false>(gl.big_geo[i], p, r);
+            uint32_t const k = key_big<false, true>(gl.big_geo[i], p, r, p.last == ns + i);
             if(k < best) {
                 best = k;
                 id = ns + i;
             }
         }
         for(int i = nbn; i < nb; ++i) {
-            uint32_t const k = key_big<true>(gl.big_geo[i], p, r);
+            uint32_t const k = key_big<true, true>(gl.big_geo[i], p, r, p.last == ns + i);
             if(k < best) {
                 best = k;
                 id = ns + i;
@@ -402,6 +442,7 @@ __device__ __forceinline__ bool shade_common(PathF32& p, bool hit, float t, int 
     p.ox = hx;
     p.oy = hy;
     p.oz = hz;
+    p.last = id;
     refl = __float_as_int(sb.w);
     return true;
 }

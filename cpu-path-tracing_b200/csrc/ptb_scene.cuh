@@ -79,10 +79,23 @@ struct CameraF32
     float sub_len;       // 1/num_subpixels
 };
 
+// camera of the stand-alone smallpt fork (sandbox/main.cpp:235-237), shifted FP32 frame
+struct SmallptCamF32
+{
+    float ox, oy, oz; // camera position
+    float dx, dy, dz; // unit viewing direction
+    float cxx;        // cx = (w * .5135 / h, 0, 0)
+    float cyx, cyy, cyz;
+    float push;       // 140
+    float inv_w, inv_h;
+    float pad_[3];
+};
+
 // Everything the FP32 kernels read through the constant cache.
 struct ConstSceneF32
 {
     CameraF32 cam;
+    SmallptCamF32 sbcam;
     int n_small_near; // small spheres tested at the near root only
     int n_small;      // all small spheres (near-only first)
     int n_big_near;

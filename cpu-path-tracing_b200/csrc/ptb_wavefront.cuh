@@ -69,7 +69,9 @@ __device__ __forceinline__ void wf_load(WfStream const& s, uint32_t i, PathF32& 
     p.dx = b.x;
     p.dy = b.y;
     p.dz = b.z;
-    p.depth = __float_as_int(b.w);
+    int const packed = __float_as_int(b.w); // depth (< 2^8) | (last + 1) << 8
+    p.depth = packed & 0xFF;
+    p.last = (packed >> 8) - 1;
     p.tr = c.x;
     p.tg = c.y;
     p.tb = c.z;
@@ -84,7 +86,7 @@ __device__ __forceinline__ void wf_load(WfStream const& s, uint32_t i, PathF32& 
 __device__ __forceinline__ void wf_store(WfStream const& s, uint32_t i, PathF32 const& p, uint32_t slot)
 {
     s.a[i] = make_float4(p.ox, p.oy, p.oz, p.len);
-    s.b[i] = make_float4(p.dx, p.dy, p.dz, __int_as_float(p.depth));
+    s.b[i] = make_float4(p.dx, p.dy, p.dz, __int_as_float(p.depth | ((p.last + 1) << 8)));
     s.c[i] = make_float4(p.tr, p.tg, p.tb, __uint_as_float(p.rng.state));
     s.d[i] = make_float4(p.er, p.eg, p.eb, __uint_as_float(p.rng.inc));
     s.slot[i] = slot;
@@ -412,9 +414,9 @@ cudaError_t launch_wavefront(WavefrontBuffers const& buf, RenderParamsF32 const&
     w.ctr = buf.counters;
     w.pool = buf.pool;
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d, bx, by, bz, uk) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk) && smem) { \
-        return wf_run<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk)>, true>(w, p, sm_count, stream, launches); \
+#define X(a, b, cc, d, bx, by, bz, uk, em) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) && smem) { \
+        return wf_run<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, true>(w, p, sm_count, stream, launches); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X

@@ -319,6 +319,46 @@ inline auto box_like(int const w, int const h, reflection_type const wall, vec3 
     return s;
 }
 
+// ---- sandbox/main.cpp (the stand-alone smallpt fork) ------------------------------------------------------
+// Its Sphere (sandbox/main.cpp:62-66) has pt::sphere's layout and material order, so the scene is a
+// std::vector<pt::sphere>; its camera is four constants in main (sandbox/main.cpp:235,260).
+struct smallpt_camera
+{
+    vec3 position{ 50, 52, 295.6 };
+    vec3 direction{ 0, -0.042612, -1 };
+    double fov_factor{ .5135 };
+    double push{ 140 };
+};
+static_assert(sizeof(smallpt_camera) == 64, "cam8 of ptb_set_smallpt_camera");
+
+// sandbox/main.cpp:94-122: six R = 1e5 wall spheres seen from inside, two mirrors, a light, a glass ball
+[[nodiscard]] inline auto smallpt_scene() -> std::vector<sphere>
+{
+    using namespace detail;
+    vec3 const none{ 0, 0, 0 };
+    vec3 const grey{ .75, .75, .75 };
+    vec3 const shiny = vec3{ 1, 1, 1 } * .999;
+    return {
+        { 1e5, { 1e5 + 1, 40.8, 81.6 }, none, { .75, .25, .25 }, D },   // left
+        { 1e5, { -1e5 + 99, 40.8, 81.6 }, none, { .25, .25, .75 }, D }, // right
+        { 1e5, { 50, 40.8, 1e5 }, none, grey, D },                      // back
+        { 1e5, { 50, 40.8, -1e5 + 170 }, none, none, D },               // front
+        { 1e5, { 50, 1e5, 81.6 }, none, grey, D },                      // bottom
+        { 1e5, { 50, -1e5 + 81.6, 81.6 }, none, { .25, .75, .15 }, D }, // top
+        { 16.5, { 27, 16.5, 47 }, none, shiny, S },                     // mirror
+        { 16.5, { 65, 16.5, 37 }, none, { 0.6, 0.1, 0.6 }, S },         // purple mirror
+        { 16.5, { 45, 46.5, 50 }, { 22, 22, 22 }, none, D },            // light
+        { 16.5, { 73, 16.5, 78 }, none, shiny, G },                     // glass
+    };
+}
+
+// toInt of sandbox/main.cpp:130-133 (rounds by adding .5, unlike pt::color_to_int's std::round)
+[[nodiscard]] inline auto smallpt_to_int(double const x) noexcept -> int
+{
+    double const c = x < 0 ? 0 : x > 1 ? 1 : x;
+    return int(std::pow(c, 1 / 2.2) * 255 + .5);
+}
+
 } // namespace pt
 
 #endif // PTB200_HOST_PT_HPP

@@ -53,3 +53,14 @@ for name, W, H, S in [("box_mirror", 1920, 1080, 16), ("box_mirror", 1920, 1080,
             paths = W * H * 4 * S
             print(f"TIMING {vname} {name} {W}x{H} samps/subpixel {S}: {st.last_render_ms:.2f} ms  {paths/st.last_render_ms/1e3:.1f} Mpaths/s "
                   f"{st.rays/st.last_render_ms/1e3:.1f} Mrays/s rays/path {st.rays/paths:.3f}")
+
+# ---- sandbox (stand-alone smallpt) mode ------------------------------------------------------------------
+sph, cam8 = pkg.builtin_smallpt_scene()
+W, H = 1024, 768
+with pkg.Renderer(0) as r:
+    r.upload_scene(sph); r.set_smallpt_camera(cam8); r.set_image(W, H, 2)
+    print("smallpt layout", r.scene_layout())
+    for S in (4, 64):
+        r.clear(); r.render(1, 0, S, pkg.INTEGRATOR_SMALLPT); st = r.stats()
+        print(f"TIMING smallpt {W}x{H} samps/subpixel {S}: {st.last_render_ms:.2f} ms {W*H*4*S/st.last_render_ms/1e3:.1f} Mpaths/s "
+              f"{st.rays/st.last_render_ms/1e3:.1f} Mrays/s rays/path {st.rays/st.paths:.3f}")

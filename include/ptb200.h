@@ -61,7 +61,13 @@ enum
     PTB_PRECISION_FP32 = 0x00, /* throughput mode (the measured mode) */
     PTB_PRECISION_FP64 = 0x10, /* deterministic parity mode: FP64, no FMA contraction,
                                   reference operation order */
-    PTB_PRECISION_MASK = 0xF0
+    PTB_PRECISION_MASK = 0xF0,
+    /* integrator: which of the reference's two programs */
+    PTB_INTEGRATOR_PT = 0x000,      /* src/main.cpp: thin-lens camera, sky, roulette after depth 4, limit 100 */
+    PTB_INTEGRATOR_SMALLPT = 0x100, /* sandbox/main.cpp (stand-alone smallpt): tent-filter pinhole camera set with
+                                       ptb_set_smallpt_camera, black miss, roulette after depth 5, IOR 1.5 glass
+                                       that splits into reflection + refraction while depth <= 2, 2x2 sub-pixels */
+    PTB_INTEGRATOR_MASK = 0xF00
 };
 
 typedef struct ptb_stats
@@ -101,6 +107,10 @@ int ptb_synchronize(ptb_context* ctx);
 int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t stride);
 /* A derived pt::camera, i.e. the result of pt::camera::with_config (src/main.cpp:209). */
 int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes);
+/* Camera of the stand-alone smallpt fork, sandbox/main.cpp:235-237,260: cam8 = position(3), viewing
+ * direction(3, need not be unit), field-of-view factor (.5135 there), push distance (140 there).
+ * cx, cy are derived from the image size like the sandbox does. */
+int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8);
 /* Image geometry: width/height of src/main.cpp:204-205, num_subpixels of :202.
  * (Re)allocates and zeroes the accumulation buffer: one float4 {r,g,b,n} of
  * un-clamped radiance SUMS per sub-pixel (slot = ((y*W+x)*ns+sy)*ns+sx). */
@@ -147,7 +157,8 @@ int ptb_get_stats(ptb_context* ctx, ptb_stats* out);
 
 /* How the FP32 path packed the uploaded scene (ptb_scene.cuh): out[0..9] = small near-only,
  * small both-roots, big near-only, big both-roots, of the big near-only: on the x / y / z
- * axis of the frame, big spheres share one radius (0/1), lists fit constant memory (0/1),
+ * axis of the frame, bit 0: big spheres share one radius | bit 1: index-in-key allowed (scene small
+ * against epsilon), lists fit constant memory (0/1),
  * a fully unrolled kernel exists for this layout (0/1). */
 int ptb_scene_layout(ptb_context* ctx, int32_t out[10]);
 
@@ -180,8 +191,13 @@ int ptb_camera_with_config(void const* camera_config, void* camera_out);
  * count, and the 112-byte camera_config.  Call with spheres_out = NULL to query the count. */
 int ptb_builtin_scene(char const* name, int width, int height, void* spheres_out, size_t capacity, size_t* count_out,
                       void* camera_config_out);
+/* The sandbox's own scene and camera constants (sandbox/main.cpp:94-122,235,260): up to `capacity`
+ * 88-byte spheres (10 of them), the count, and cam8 for ptb_set_smallpt_camera. */
+int ptb_builtin_smallpt_scene(void* spheres_out, size_t capacity, size_t* count_out, double* cam8_out);
 /* ASCII PPM "P3" writer with gamma 2.2, byte-compatible with src/main.cpp:240-247. */
 int ptb_write_ppm(char const* path, double const* rgb, int width, int height);
+/* Same, with the sandbox's rounding: int(pow(clamp(x), 1/2.2) * 255 + .5), sandbox/main.cpp:130-133,271-275. */
+int ptb_write_ppm_smallpt(char const* path, double const* rgb, int width, int height);
 
 #ifdef __cplusplus
 }

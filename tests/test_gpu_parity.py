@@ -359,7 +359,7 @@ def test_error_behaviour(gpu):
             r.set_image(0, 8, 2)
         r.set_image(8, 8, 2)
         with pytest.raises(gpu.PtbError) as e:
-            r.render(1, 0, 1, 0x100)  # unknown flag
+            r.render(1, 0, 1, 0x1000)  # unknown flag
         assert e.value.code == -1
         with pytest.raises(gpu.PtbError):
             r.render(1, 0xFFFFFFFF, 2)  # sample range overflow
