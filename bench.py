@@ -47,6 +47,8 @@ CONFIGS = {
     "C3": ("box_mirror", 1920, 1080, 4096),
     "C4": ("dof_glass", 3840, 2160, 4096),
     "C5": ("spheres10k", 1920, 1080, 1024),
+    # the reference's stand-alone smallpt fork, sandbox/main.cpp: its own scene, 1024x768
+    "SB": ("smallpt", 1024, 768, 4096),
 }
 SEED = 1
 
@@ -124,10 +126,18 @@ def cpu_reference_rate(scene, width, height, samps, kind_pref=("ref_stock", "por
     from __graft_entry__ import load_package
 
     pkg = load_package()
-    spheres, cfg = pkg.builtin_scene(scene, width, height)  # host-side scene layer only (no GPU)
-    cam = pkg.camera_with_config(cfg)
     cores = os.cpu_count() or 1
     paths = width * height * 4 * samps
+    if scene == "smallpt":
+        spheres, cam8 = pkg.builtin_smallpt_scene()
+        kind = "reference" if available("ref_sandbox") else "port"
+        orc = Oracle("ref_sandbox" if kind == "reference" else "port")
+        t0 = time.perf_counter()
+        orc.sb_render(spheres, cam8, width, height, samps, mode=0, nthreads=cores)  # the program's own erand48 stream
+        dt = time.perf_counter() - t0
+        return paths / dt / 1e6, kind, cores, dt
+    spheres, cfg = pkg.builtin_scene(scene, width, height)  # host-side scene layer only (no GPU)
+    cam = pkg.camera_with_config(cfg)
     if "ref_stock" in kind_pref and available("ref_stock"):
         orc = Oracle("ref_stock")
         t0 = time.perf_counter()
@@ -148,6 +158,8 @@ def oracle_statistics(scene, width, height):
 
     pkg = load_package()
     w, h = max(64, width // 8), max(48, height // 8)
+    if scene == "smallpt":
+        return None, 10  # the sandbox restatement keeps no statistics: flop model from the GPU counters
     spheres, cfg = pkg.builtin_scene(scene, w, h)
     cam = pkg.camera_with_config(cfg)
     orc = Oracle("port")
@@ -222,10 +234,17 @@ def main():
     torch.cuda.set_device(local)
     flags = pkg.PRECISION_FP32 | (pkg.VARIANT_WAVEFRONT if args.variant == "wavefront" else pkg.VARIANT_MEGAKERNEL)
 
-    spheres, cfg = pkg.builtin_scene(scene, width, height)
-    cam = pkg.camera_with_config(cfg)
     dr = DistributedRenderer(pkg, local, rank, world)
-    dr.setup(spheres, cam, width, height, 2)
+    if scene == "smallpt":
+        spheres, cam = pkg.builtin_smallpt_scene()  # cam = cam8
+        flags |= pkg.INTEGRATOR_SMALLPT
+        dr.setup(spheres, None, width, height, 2, smallpt_camera=cam)
+        set_camera = dr.renderer.set_smallpt_camera
+    else:
+        spheres, cfg = pkg.builtin_scene(scene, width, height)
+        cam = pkg.camera_with_config(cfg)
+        dr.setup(spheres, cam, width, height, 2)
+        set_camera = dr.renderer.set_camera
     r = dr.renderer
 
     def barrier():
@@ -278,7 +297,7 @@ def main():
 
     def e2e_step():
         r.upload_scene(spheres)
-        r.set_camera(cam)
+        set_camera(cam)
         dr.step(SEED, samps, flags, resolve=False)
         if rank == 0:
             r.resolve_into(pinned)
@@ -301,7 +320,16 @@ def main():
     if rank == 0:
         peak_tflops = r.measure_fp32_peak()
         ostats, n_spheres = oracle_statistics(scene, width, height)
-        fpp = flop_per_path(ostats, n_spheres)
+        if ostats is None:
+            # sandbox scene: same per-operation constants, event counts from the GPU counters of this run
+            # (no sky; ~1/3 of the 10 sphere tests reach the root stage, measured on the src/ scenes)
+            rpp = rays_per_path
+            hits = {k: getattr(st, "hits_" + k) / max(st.paths, 1) for k in ("diffuse", "specular", "dielectric")}
+            fpp = (rpp * (FLOP_RAY_FIXED + n_spheres * (FLOP_TEST + 0.66 * FLOP_ROOT + 0.33 * FLOP_ROOT2)) + FLOP_SHADE * rpp
+                   + FLOP_DIFFUSE * hits["diffuse"] + FLOP_SPECULAR * hits["specular"]
+                   + (FLOP_DIELECTRIC + FLOP_REFRACT) * hits["dielectric"] + FLOP_PRIMARY)
+        else:
+            fpp = flop_per_path(ostats, n_spheres)
         # the dominant kernel = the megakernel; its average launch duration from the library's own events
         k_ms = sum(kernel_ms) / len(kernel_ms)
         paths_per_launch = width * height * 4 * my_count
@@ -315,7 +343,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.config}: {scene} {width}x{height} @ {spp} spp (BASELINE.json configs[{int(args.config[1]) - 1}])",
+                "workload": f"{args.config}: {scene} {width}x{height} @ {spp} spp "
+                            + (f"(BASELINE.json configs[{int(args.config[1]) - 1}])" if args.config[0] == "C" else "(sandbox/main.cpp, SURVEY 8 f-1)"),
                 "variant": args.variant, "samples_per_subpixel": samps, "spheres": int(len(spheres)),
                 "partition": f"samples of every sub-pixel split over {world} GPU(s); NCCL sum-reduce to rank 0" if world > 1
                 else "single GPU",

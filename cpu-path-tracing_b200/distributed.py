@@ -49,12 +49,16 @@ class DistributedRenderer:
         self.renderer = pkg.Renderer(device)
         self.accum = None
 
-    def setup(self, spheres, camera, width: int, height: int, nsub: int = 2):
+    def setup(self, spheres, camera, width: int, height: int, nsub: int = 2, smallpt_camera=None):
+        """camera: a 176-byte pt::camera (src/ integrator) and/or smallpt_camera: cam8 (sandbox integrator)."""
         torch = self.torch
         r = self.renderer
         r.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         r.upload_scene(spheres)
-        r.set_camera(camera)
+        if camera is not None:
+            r.set_camera(camera)
+        if smallpt_camera is not None:
+            r.set_smallpt_camera(smallpt_camera)
         r.set_image(width, height, nsub)
         self.accum = torch.zeros((width * height * nsub * nsub, 4), dtype=torch.float32, device=self.device)
         r.set_accum_buffer(self.accum.data_ptr(), self.accum.numel() * 4)
