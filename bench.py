@@ -204,7 +204,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--spp", type=int, default=0, help="override the config's total samples per pixel")
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront"])
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "sorted"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -232,7 +232,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    flags = pkg.PRECISION_FP32 | (pkg.VARIANT_WAVEFRONT if args.variant == "wavefront" else pkg.VARIANT_MEGAKERNEL)
+    flags = pkg.PRECISION_FP32 | {"mega": pkg.VARIANT_MEGAKERNEL, "wavefront": pkg.VARIANT_WAVEFRONT,
+                                  "sorted": pkg.VARIANT_MEGAKERNEL_SORTED}[args.variant]
 
     dr = DistributedRenderer(pkg, local, rank, world)
     if scene == "smallpt":

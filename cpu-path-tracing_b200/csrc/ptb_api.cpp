@@ -59,6 +59,10 @@ struct ptb_context
     uint8_t* d_rgb8 = nullptr;
 
     DeviceCounters* d_counters = nullptr;
+    // material scattered in place by the sorted megakernel (0 diffuse, 1 specular): a guess from the geometry at
+    // upload, then whichever of the two the previous sorted launch hit more often
+    int inline_material = 1;
+    unsigned long long seen_diffuse = 0, seen_specular = 0; // counter values already accounted for
     WavefrontBuffers wf{ nullptr, nullptr, nullptr, 0 };
     ptb_stats stats{};
 };
@@ -308,7 +312,8 @@ PackedScene pack_geometry(ptb_context* ctx)
         b.x = static_cast<float>(s[i].er);
         b.y = static_cast<float>(s[i].eg);
         b.z = static_cast<float>(s[i].eb);
-        int32_t const refl = s[i].reflection;
+        bool const emits = s[i].er != 0.0 || s[i].eg != 0.0 || s[i].eb != 0.0;
+        int32_t const refl = s[i].reflection | (emits ? 0x100 : 0); // kEmissiveBit, ptb_mega_sorted.cuh
         std::memcpy(&b.w, &refl, sizeof(float));
         c.x = static_cast<float>(s[i].cr);
         c.y = static_cast<float>(s[i].cg);
@@ -317,7 +322,7 @@ PackedScene pack_geometry(ptb_context* ctx)
         d.x = static_cast<float>(s[i].cr * inv_p);
         d.y = static_cast<float>(s[i].cg * inv_p);
         d.z = static_cast<float>(s[i].cb * inv_p);
-        d.w = 0.0f;
+        d.w = static_cast<float>(p); // so that the roulette needs one plane: (color/p, p)
         size_t const P = static_cast<size_t>(pos);
         out.shade[P] = a;
         out.shade[N + P] = b;
@@ -645,6 +650,15 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
     PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_spheres, ctx->h_spheres.data(), count * sizeof(RawSphere),
                                   cudaMemcpyHostToDevice, ctx->stream));
     ctx->have_scene = true;
+    {
+        // first guess for the sorted megakernel: surface seen by a ray ~ radius^2, walls (huge spheres) capped
+        double w[3] = { 0.0, 0.0, 0.0 };
+        for(RawSphere const& sp : ctx->h_spheres) {
+            double const r = std::min(std::fabs(sp.radius), 4.0);
+            w[sp.reflection] += r * r;
+        }
+        ctx->inline_material = w[1] >= w[0] ? 1 : 0;
+    }
     return rebuild_device_scene(ctx);
 }
 
@@ -753,6 +767,7 @@ int ptb_clear(ptb_context* ctx)
     ctx->accum64_used = false;
     PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), ctx->stream));
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->seen_diffuse = ctx->seen_specular = 0;
     uint64_t const launches = ctx->stats.kernel_launches;
     ctx->stats = ptb_stats{};
     ctx->stats.kernel_launches = launches;
@@ -767,7 +782,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     uint32_t const variant = flags & PTB_VARIANT_MASK;
     uint32_t const precision = flags & PTB_PRECISION_MASK;
     uint32_t const integrator = flags & PTB_INTEGRATOR_MASK;
-    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK)) != 0 || variant > PTB_VARIANT_WAVEFRONT ||
+    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK)) != 0 || variant > PTB_VARIANT_MEGAKERNEL_SORTED ||
        (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) ||
        (integrator != PTB_INTEGRATOR_PT && integrator != PTB_INTEGRATOR_SMALLPT)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
@@ -777,7 +792,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     if(rc != PTB_OK) {
         return rc;
     }
-    if(smallpt && (variant == PTB_VARIANT_WAVEFRONT || ctx->ns != 2)) {
+    if(smallpt && (variant != PTB_VARIANT_MEGAKERNEL || ctx->ns != 2)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: the smallpt integrator is megakernel-only and uses 2x2 sub-pixels (sandbox/main.cpp:248-249)");
     }
     if(variant == PTB_VARIANT_WAVEFRONT && precision == PTB_PRECISION_FP64) {
@@ -846,6 +861,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         p.shade = shade_planes(ctx);
         p.geo = geo_lists(ctx);
         p.n_total = ctx->n;
+        p.key_mask = ~((1u << 4) - 1u); // kIdBits of ptb_path_f32.cuh
         if(variant == PTB_VARIANT_WAVEFRONT) {
             uint64_t const items = static_cast<uint64_t>(p.nslots) * p.samples;
             uint32_t const pool = static_cast<uint32_t>(std::min<uint64_t>(1ull << 22, std::max<uint64_t>(items, 1024)));
@@ -866,6 +882,13 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
             buf.pool = pool;
             PTB_CUDA(ctx, launch_wavefront(buf, p, ctx->counts, ctx->sm_count, st, &launches));
         }
+        else if(variant == PTB_VARIANT_MEGAKERNEL_SORTED) {
+            int inline_material = ctx->inline_material;
+            if(char const* force = std::getenv("PTB_INLINE_MATERIAL")) { // experiments (dev/)
+                inline_material = std::atoi(force) == 0 ? 0 : 1;
+            }
+            PTB_CUDA(ctx, launch_megakernel_sorted(p, ctx->counts, ctx->sm_count, st, &launches, inline_material));
+        }
         else {
             PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches, smallpt));
         }
@@ -878,6 +901,18 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     ctx->stats.total_render_ms += ms;
     ctx->stats.kernel_launches += static_cast<uint64_t>(launches);
     ctx->stats.paths += static_cast<uint64_t>(ctx->nslots) * samples_per_subpixel;
+    if(variant == PTB_VARIANT_MEGAKERNEL_SORTED && precision == PTB_PRECISION_FP32) {
+        // feedback for the next launch: which of diffuse / specular did this one hit more often (32 bytes, stream is idle)
+        DeviceCounters c{};
+        PTB_CUDA(ctx, cudaMemcpy(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        unsigned long long const nd = c.diffuse - std::min(c.diffuse, ctx->seen_diffuse);
+        unsigned long long const nsp = c.specular - std::min(c.specular, ctx->seen_specular);
+        if(nd + nsp > 0) {
+            ctx->inline_material = nsp >= nd ? 1 : 0;
+        }
+        ctx->seen_diffuse = c.diffuse;
+        ctx->seen_specular = c.specular;
+    }
     return PTB_OK;
 }
 

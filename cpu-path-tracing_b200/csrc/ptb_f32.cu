@@ -21,6 +21,8 @@
 //   * a finished path adds {r,g,b,1} to its slot with ONE 16-byte vector reduction
 //     (red.global.add.v4.f32, sm_90+): no read-modify-write, no per-thread image
 //     state, progressive by construction.
+#include <cstdlib>
+
 #include "ptb_kernels.h"
 #include "ptb_path_f32.cuh"
 #include "ptb_smallpt_f32.cuh"
@@ -303,6 +305,10 @@ static cudaError_t launch_one(RenderParamsF32 const& p, int sm_count, cudaStream
     if(per_sm < 1) {
         per_sm = 1;
     }
+    if(char const* cap = std::getenv("PTB_BLOCKS_PER_SM")) { // occupancy experiments (dev/)
+        int const v = std::atoi(cap);
+        per_sm = v >= 1 && v < per_sm ? v : per_sm;
+    }
     unsigned long long blocks = static_cast<unsigned long long>(sm_count) * static_cast<unsigned long long>(per_sm);
     unsigned long long const blocks_needed =
         (static_cast<unsigned long long>(p.ntiles) + (kMegaThreads / 32) - 1) / (kMegaThreads / 32);
@@ -348,6 +354,7 @@ cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, in
 
 } // namespace ptb
 
+#include "ptb_mega_sorted.cuh"
 #include "ptb_wavefront.cuh"
 
 namespace ptb {

@@ -38,6 +38,7 @@ struct RenderParamsF32
     ShadePlanes shade;      // global-memory shading planes
     GeoLists geo;           // global-memory geometry lists (generic variant)
     int n_total;
+    uint32_t key_mask;      // ~(2^kIdBits - 1), handed over as DATA so that it lives in a register (see closest_hit)
 };
 
 // Copy the packed scene into the constant bank the FP32 kernels read.
@@ -57,6 +58,10 @@ bool megakernel_has_specialisation(SceneCounts const& c);
 // Launch the persistent megakernel: grid = SM count * resident blocks.
 cudaError_t launch_megakernel(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
                               int* launches, bool smallpt);
+
+// The material-sorted megakernel (ptb_mega_sorted.cuh): src/main.cpp integrator only.
+cudaError_t launch_megakernel_sorted(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
+                                     int* launches, int inline_material);
 
 // ---- wavefront / material-sorted variant (ptb_wavefront.cuh) ------------------------------------------
 struct WavefrontCounters

@@ -1,0 +1,422 @@
+// ptb_mega_sorted.cuh -- the material-sorted megakernel (included by ptb_f32.cu).
+//
+// Same job as mega_kernel (ptb_f32.cu): the row tasks of /root/reference/src/main.cpp:217-236,
+// one persistent launch, warps pulling tiles from a global cursor.  What changes is WHERE the
+// three-way material branch of main.cpp:141-154 runs.
+//
+// Measured on mega_kernel (profiles/r1_mega_v3_box_mirror_ncu.md): the closest-hit scan issues
+// at 31.8 of 32 lanes, but everything after it diverges -- diffuse_ray (58 instructions) runs
+// on 63 % of the loop iterations at 2.2 lanes, dielectric_ray at 3.3 lanes, together ~22 % of
+// all issue slots for ~12 % of the bounces.  Here a warp keeps two rings of complete path
+// states in shared memory:
+//
+//   READY  rays waiting for a closest-hit query (fresh camera samples and scattered paths)
+//   PARK   paths whose hit needs diffuse_ray / dielectric_ray
+//
+// Per loop iteration every lane holds one ray in registers: scan (all lanes), the part of the
+// bounce that is the same for all materials (hit record, emission, Russian roulette), then
+//   - a hit on the scene's DOMINANT material (template parameter kInline: mirror in box_mirror --
+//     80 % of the bounces -- diffuse in the plain box; chosen by the host from the previous
+//     launch's counters) scatters in place,
+//   - any other surviving hit is PARKED (four 16-byte shared stores) and the lane takes the
+//     next READY ray,
+//   - when 32 paths are parked the whole warp scatters them at once -- one entry per lane,
+//     all lanes busy -- and appends them to READY.
+// Camera samples are generated 32 at a time into READY as before.  The random stream is keyed
+// by (seed, slot, sample) and travels with the path, so the image does not depend on any of this.
+//
+// Emission leaves the path state: a hit on an emitting sphere adds throughput * emission to the
+// slot straight away (red.global.add.v4.f32 with weight 0) and the path's end adds the weight 1,
+// so a parked path is 14 words -- four float4 planes.
+//
+// Ring accounting (all warp-uniform): tokens = lanes + READY + PARK.  Camera samples are only
+// generated when READY + PARK <= 32, so tokens <= 96.  Loop order: refill, pop, scatter stage
+// (whenever PARK >= 32), bounce.  With 64-entry rings neither ring can overflow: see the scatter stage.
+#pragma once
+
+namespace ptb {
+
+constexpr int kSortedThreads = 128;
+constexpr int kSortedBlocksPerSm = 6;
+constexpr int kSortedRing = 64; // entries per ring, power of two
+constexpr int kEmissiveBit = 0x100; // in ShadePlanes::b.w next to the reflection tag (ptb_api.cpp: pack_geometry)
+
+struct WarpPool
+{
+    // one path per entry, both rings:
+    //   a = origin xyz, len           b = direction xyz, slot
+    //   c = throughput rgb, last      d = rng.state, rng.inc, depth | material << 8, -
+    float4 ra[kSortedRing], rb[kSortedRing], rc[kSortedRing], rd[kSortedRing];
+    float4 pa[kSortedRing], pb[kSortedRing], pc[kSortedRing], pd[kSortedRing];
+};
+
+// the four shading planes as one array: plane k of sphere i = base[k * stride + i]
+template<bool kSmem>
+struct ShadeArray
+{
+    float4 const* base;
+    int stride_rt;
+    __device__ __forceinline__ float4 get(int plane, int id) const
+    {
+        return base[plane * (kSmem ? kSmemShadeSpheres : stride_rt) + id];
+    }
+};
+
+template<class Shape, bool kSmemShade, int kInline>
+__global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorted_kernel(RenderParamsF32 const prm)
+{
+    __shared__ float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
+    __shared__ WarpPool s_pool[kSortedThreads / 32];
+    ShadeArray<kSmemShade> sh{ prm.shade.a, prm.n_total }; // the global planes are contiguous (ptb_api.cpp: shade_planes)
+    if constexpr(kSmemShade) {
+        for(int i = threadIdx.x; i < prm.n_total; i += kSortedThreads) {
+            s_shade[i] = prm.shade.a[i];
+            s_shade[kSmemShadeSpheres + i] = prm.shade.b[i];
+            s_shade[2 * kSmemShadeSpheres + i] = prm.shade.c[i];
+            s_shade[3 * kSmemShadeSpheres + i] = prm.shade.d[i];
+        }
+        __syncthreads();
+        sh.base = s_shade;
+    }
+
+    constexpr uint32_t kFull = 0xffffffffu;
+    constexpr uint32_t kWrap = kSortedRing - 1;
+    uint32_t const lane = threadIdx.x & 31u;
+    uint32_t const lt_mask = (1u << lane) - 1u;
+    WarpPool& pool = s_pool[threadIdx.x >> 5];
+    float const k_uniform = Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f;
+    uint32_t const keep_reg = prm.key_mask; // see closest_hit: a run-time value so that it stays in a register
+
+    // warp-uniform state
+    uint32_t tile_sample0 = 0, tile_samples = 0, next_sample = 0;
+    uint32_t ready_head = 0, ready_tail = 0, ready_count = 0;
+    uint32_t park_head = 0, park_tail = 0, park_count = 0;
+    bool exhausted = false;
+    // per lane: the sub-pixel this lane generates camera samples for in the current tile
+    uint32_t gen_slot = 0, gen_valid = 0, gen_x = 0, gen_y = 0, gen_sx = 0, gen_sy = 0;
+
+    // Which lanes hold a ray is kept as a warp-uniform mask: "who needs a ray" costs no vote, and the
+    // common case -- every lane busy -- is one compare.
+    uint32_t am = 0u;
+    uint32_t slot = 0;
+    PathF32 p;
+    p.er = p.eg = p.eb = 0.0f; // unused here: emission is flushed where it is picked up
+    p.ox = p.oy = p.oz = p.dx = p.dy = p.dz = p.len = p.tr = p.tg = p.tb = 0.0f;
+    p.rng.state = p.rng.inc = 0u;
+    p.depth = 0;
+    p.last = -1;
+    BounceCounters cnt{ 0, 0, 0, 0 };
+
+    for(;;) {
+        // ---- refill: one camera sample per lane (main.cpp:186-190, camera.cpp:19-38) -----------------
+        if(!exhausted && ready_count + park_count <= 32u) {
+            __syncwarp(); // ring entries read by earlier pops are about to be overwritten
+            if(next_sample >= tile_samples) {
+                unsigned long long t = 0;
+                if(lane == 0) {
+                    t = atomicAdd(&prm.counters->tile_cursor, 1ull);
+                }
+                t = __shfl_sync(kFull, t, 0);
+                if(t >= prm.ntiles) {
+                    exhausted = true;
+                }
+                else {
+                    uint32_t const tile = static_cast<uint32_t>(t);
+                    uint32_t const group = tile / prm.nchunks;
+                    uint32_t const chunk = tile - group * prm.nchunks;
+                    tile_sample0 = chunk * prm.chunk;
+                    tile_samples = min(prm.chunk, prm.samples - tile_sample0);
+                    next_sample = 0;
+                    gen_slot = group * 32u + lane;
+                    gen_valid = min(32u, prm.nslots - group * 32u); // the slots of a tile are a prefix of its lanes
+                    if(lane < gen_valid) {
+                        slot_coords(gen_slot, prm.width, prm.ns, gen_x, gen_y, gen_sx, gen_sy);
+                    }
+                }
+            }
+            if(!exhausted) {
+                if(lane < gen_valid) {
+                    PathF32 g;
+                    g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
+                    gen_primary(g, c_scene.cam, gen_x, gen_y, gen_sx, gen_sy);
+                    uint32_t const w = (ready_head + lane) & kWrap;
+                    pool.ra[w] = make_float4(g.ox, g.oy, g.oz, g.len);
+                    pool.rb[w] = make_float4(g.dx, g.dy, g.dz, __uint_as_float(gen_slot));
+                    pool.rc[w] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
+                    pool.rd[w] = make_float4(__uint_as_float(g.rng.state), __uint_as_float(g.rng.inc), __int_as_float(0), 0.0f);
+                }
+                ready_head = (ready_head + gen_valid) & kWrap;
+                ready_count += gen_valid;
+                next_sample += 1u;
+                __syncwarp();
+            }
+        }
+
+        // ---- lanes without a ray take the oldest READY entries ----------------------------------
+        uint32_t const need = ~am;
+        if(need != 0u && ready_count != 0u) {
+            uint32_t const rank = __popc(need & lt_mask);
+            bool const take = ((need >> lane) & 1u) != 0u && rank < ready_count;
+            if(take) {
+                uint32_t const rd = (ready_tail + rank) & kWrap;
+                float4 const ea = pool.ra[rd];
+                float4 const eb = pool.rb[rd];
+                float4 const ec = pool.rc[rd];
+                float4 const ed = pool.rd[rd];
+                p.ox = ea.x;
+                p.oy = ea.y;
+                p.oz = ea.z;
+                p.len = ea.w;
+                p.dx = eb.x;
+                p.dy = eb.y;
+                p.dz = eb.z;
+                slot = __float_as_uint(eb.w);
+                p.tr = ec.x;
+                p.tg = ec.y;
+                p.tb = ec.z;
+                p.last = __float_as_int(ec.w);
+                p.rng.state = __float_as_uint(ed.x);
+                p.rng.inc = __float_as_uint(ed.y);
+                p.depth = __float_as_int(ed.z);
+            }
+            uint32_t const wanted = static_cast<uint32_t>(__popc(need));
+            uint32_t const taken = min(wanted, ready_count);
+            ready_tail = (ready_tail + taken) & kWrap;
+            ready_count -= taken;
+            am = taken == wanted ? kFull : (am | __ballot_sync(kFull, take));
+        }
+
+        // ---- scatter stage: diffuse_ray / dielectric_ray for up to 32 parked paths, one per lane ----
+        // Runs AFTER the pop: with every lane holding a ray, tokens <= 96 gives READY <= 32 whenever PARK >= 32
+        // (room for the 32 results), and a lane still without a ray means READY is empty.  It leaves PARK < 32,
+        // so the bounce below may park all 32 lanes.
+        if(park_count >= 32u || (am != kFull && exhausted && ready_count == 0u && park_count != 0u)) {
+            __syncwarp(); // the parked entries were written by other lanes
+            uint32_t const k = min(32u, park_count);
+            if(lane < k) {
+                uint32_t const rd = (park_tail + lane) & kWrap;
+                float4 const ea = pool.pa[rd];
+                float4 const eb = pool.pb[rd];
+                float4 const ec = pool.pc[rd];
+                float4 const ed = pool.pd[rd];
+                PathF32 q;
+                q.ox = ea.x;
+                q.oy = ea.y;
+                q.oz = ea.z;
+                q.len = ea.w;
+                q.dx = eb.x;
+                q.dy = eb.y;
+                q.dz = eb.z;
+                q.rng.state = __float_as_uint(ed.x);
+                q.rng.inc = __float_as_uint(ed.y);
+                int const last = __float_as_int(ec.w);
+                int const dm = __float_as_int(ed.z);
+                // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6)
+                float4 const sa = sh.get(0, last);
+                float const nx = fmaf(q.ox, sa.w, sa.x);
+                float const ny = fmaf(q.oy, sa.w, sa.y);
+                float const nz = fmaf(q.oz, sa.w, sa.z);
+                float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
+                int const mat = dm >> 8;
+                if(mat == 0) {
+                    cnt.diffuse++;
+                    bool const front = dn < 0.0f; // hit_record.cpp:7
+                    scatter_diffuse(q, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
+                }
+                else if(mat == 1) {
+                    cnt.specular++;
+                    reflect_ray(q, nx, ny, nz);
+                }
+                else {
+                    cnt.dielectric++;
+                    scatter_dielectric(q, nx, ny, nz, dn);
+                }
+                uint32_t const w = (ready_head + lane) & kWrap;
+                pool.ra[w] = make_float4(q.ox, q.oy, q.oz, q.len);
+                pool.rb[w] = make_float4(q.dx, q.dy, q.dz, eb.w);
+                pool.rc[w] = ec;
+                pool.rd[w] = make_float4(__uint_as_float(q.rng.state), __uint_as_float(q.rng.inc),
+                                         __int_as_float((dm & 0xff) + 1), 0.0f); // main.cpp:111 ++depth
+            }
+            park_tail = (park_tail + k) & kWrap;
+            park_count -= k;
+            ready_head = (ready_head + k) & kWrap;
+            ready_count += k;
+            __syncwarp();
+            if(am != kFull) {
+                continue; // hand the fresh rays to the lanes that wait for one
+            }
+        }
+        if(am == 0u) {
+            if(exhausted && ready_count == 0u && park_count == 0u) {
+                break;
+            }
+            continue;
+        }
+
+        // ---- one bounce: main.cpp:111-155; the material branch runs here only for material kInline ----------
+        bool park = false;
+        bool alive = ((am >> lane) & 1u) != 0u;
+        int material = 0;
+        if(alive) {
+            RayTerms const r = ray_terms(p, k_uniform);
+            float t;
+            int id;
+            bool const hit = closest_hit<Shape, true>(c_scene, prm.geo, p, r, t, id, keep_reg);
+            cnt.rays++;
+            float fr = 0.0f, fg = 0.0f, fb = 0.0f; // radiance picked up by this bounce
+            bool flush = false, ended = false;
+            float4 sa = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if(!hit) {
+                // main.cpp:116-119 sky gradient on the unit direction
+                float const tt = 0.5f * (p.dy + 1.0f);
+                float const omt = 1.0f - tt;
+                fr = p.tr * fmaf(0.5f, tt, omt);
+                fg = p.tg * fmaf(0.7f, tt, omt);
+                fb = p.tb * (omt + tt);
+                ended = true;
+            }
+            else {
+                sa = sh.get(0, id);
+                float4 const sb = sh.get(1, id);
+                int const tag = __float_as_int(sb.w);
+                material = tag & 0xff;
+                // hit_record.cpp:5-6
+                p.ox = fmaf(p.dx, t, p.ox);
+                p.oy = fmaf(p.dy, t, p.oy);
+                p.oz = fmaf(p.dz, t, p.oz);
+                p.last = id;
+                if((tag & kEmissiveBit) != 0) { // main.cpp:126
+                    fr = p.tr * sb.x;
+                    fg = p.tg * sb.y;
+                    fb = p.tb * sb.z;
+                    flush = true;
+                }
+                // main.cpp:128-139 Russian roulette: p = max(color), survivor weight color / p
+                bool const roulette = p.depth > kRouletteThreshold;
+                float4 const col = sh.get(roulette ? 3 : 2, id);
+                if(roulette) {
+                    ended = !(rng_uniform_f32(p.rng) < col.w);
+                }
+                p.tr *= col.x;
+                p.tg *= col.y;
+                p.tb *= col.z;
+                if(!ended && p.depth >= kDepthLimit - 1) {
+                    // the ray scattered by the last iteration is never traced (main.cpp:111): count the hit, stop
+                    cnt.diffuse += material == 0 ? 1u : 0u;
+                    cnt.specular += material == 1 ? 1u : 0u;
+                    cnt.dielectric += material == 2 ? 1u : 0u;
+                    ended = true;
+                }
+            }
+            if(flush || ended) {
+                red_add_v4(prm.accum + slot, fr, fg, fb, ended ? 1.0f : 0.0f);
+            }
+            if(!ended) {
+                if(material == kInline) {
+                    float const nx = fmaf(p.ox, sa.w, sa.x); // outward normal (P - c) / R, hit_record.cpp:6
+                    float const ny = fmaf(p.oy, sa.w, sa.y);
+                    float const nz = fmaf(p.oz, sa.w, sa.z);
+                    if constexpr(kInline == 1) {
+                        cnt.specular++;
+                        reflect_ray(p, nx, ny, nz); // specular_ray, main.cpp:60-67
+                    }
+                    else {
+                        cnt.diffuse++;
+                        bool const front = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz)) < 0.0f; // hit_record.cpp:7
+                        scatter_diffuse(p, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
+                    }
+                    p.depth++;
+                }
+                else {
+                    park = true;
+                }
+            }
+            alive = !(ended || park);
+        }
+
+        // ---- park what needs one of the other scatter functions ------------------------------------------
+        am = __ballot_sync(kFull, alive);
+        uint32_t const pm = __ballot_sync(kFull, park);
+        if(pm != 0u) {
+            if(park) {
+                uint32_t const w = (park_head + __popc(pm & lt_mask)) & kWrap;
+                pool.pa[w] = make_float4(p.ox, p.oy, p.oz, p.len);
+                pool.pb[w] = make_float4(p.dx, p.dy, p.dz, __uint_as_float(slot));
+                pool.pc[w] = make_float4(p.tr, p.tg, p.tb, __int_as_float(p.last));
+                pool.pd[w] = make_float4(__uint_as_float(p.rng.state), __uint_as_float(p.rng.inc),
+                                         __int_as_float(p.depth | (material << 8)), 0.0f);
+            }
+            uint32_t const n = __popc(pm);
+            park_head = (park_head + n) & kWrap;
+            park_count += n;
+        }
+    }
+
+    uint32_t const rays = warp_sum(cnt.rays);
+    uint32_t const nd = warp_sum(cnt.diffuse);
+    uint32_t const nsp = warp_sum(cnt.specular);
+    uint32_t const ndi = warp_sum(cnt.dielectric);
+    if(lane == 0) {
+        atomicAdd(&prm.counters->rays, static_cast<unsigned long long>(rays));
+        atomicAdd(&prm.counters->diffuse, static_cast<unsigned long long>(nd));
+        atomicAdd(&prm.counters->specular, static_cast<unsigned long long>(nsp));
+        atomicAdd(&prm.counters->dielectric, static_cast<unsigned long long>(ndi));
+    }
+}
+
+template<class Shape, bool kSmem, int kInline>
+static cudaError_t launch_sorted_one(RenderParamsF32 const& p, int sm_count, cudaStream_t stream)
+{
+    int per_sm = 0;
+    cudaError_t e =
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_sorted_kernel<Shape, kSmem, kInline>, kSortedThreads, 0);
+    if(e != cudaSuccess) {
+        return e;
+    }
+    per_sm = per_sm < 1 ? 1 : per_sm;
+    if(char const* cap = std::getenv("PTB_BLOCKS_PER_SM")) { // occupancy experiments (dev/)
+        int const v = std::atoi(cap);
+        per_sm = v >= 1 && v < per_sm ? v : per_sm;
+    }
+    unsigned long long blocks = static_cast<unsigned long long>(sm_count) * static_cast<unsigned long long>(per_sm);
+    unsigned long long const blocks_needed =
+        (static_cast<unsigned long long>(p.ntiles) + (kSortedThreads / 32) - 1) / (kSortedThreads / 32);
+    blocks = blocks > blocks_needed ? blocks_needed : blocks;
+    blocks = blocks < 1 ? 1 : blocks;
+    mega_sorted_kernel<Shape, kSmem, kInline><<<static_cast<unsigned>(blocks), kSortedThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template<int kInline>
+static cudaError_t launch_sorted_inline(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream)
+{
+    bool const smem = p.n_total <= kSmemShadeSpheres;
+#define X(a, b, cc, d, bx, by, bz, uk, em) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) && smem) { \
+        return launch_sorted_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, true, kInline>(p, sm_count, stream); \
+    }
+    PTB_MEGA_SPECIALISATIONS(X)
+#undef X
+    if(smem) {
+        return launch_sorted_one<GenericShape, true, kInline>(p, sm_count, stream);
+    }
+    return launch_sorted_one<GenericShape, false, kInline>(p, sm_count, stream);
+}
+
+// inline_material: 0 = diffuse_ray runs in place, 1 = specular_ray runs in place; the other two are sorted
+// through the PARK ring.  Any value gives the same image; the right one is the scene's commonest material.
+cudaError_t launch_megakernel_sorted(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream,
+                                     int* launches, int inline_material)
+{
+    cudaError_t e = cudaMemsetAsync(&p.counters->tile_cursor, 0, sizeof(unsigned long long), stream);
+    if(e != cudaSuccess) {
+        return e;
+    }
+    if(launches != nullptr) {
+        *launches += 1;
+    }
+    return inline_material == 0 ? launch_sorted_inline<0>(p, c, sm_count, stream) : launch_sorted_inline<1>(p, c, sm_count, stream);
+}
+
+} // namespace ptb

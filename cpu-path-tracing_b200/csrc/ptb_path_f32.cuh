@@ -277,9 +277,12 @@ using GenericShape = SceneShape<-1, -1, -1, -1>;
 //    (compare/select ops are half-rate on B200).  Cost: t is truncated by < 2^-19
 //    relative, towards the ray origin.  Equal keys fall to the lower list position.
 //  - generic shape: run-time counts, geometry from global memory (any scene size).
-template<class Shape>
+// kKeepReg: the mantissa mask comes in a REGISTER (keep_reg, loaded once per kernel through an opaque move) so
+// that "(key & mask) | position" is a single three-input LOP3 with the position as its immediate; with both as
+// immediates the compiler needs two LOP3 per sphere.
+template<class Shape, bool kKeepReg = false>
 __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists const& gl, PathF32 const& p,
-                                            RayTerms const& r, float& t_out, int& id_out)
+                                            RayTerms const& r, float& t_out, int& id_out, uint32_t keep_reg = 0u)
 {
     uint32_t best = kNoHitBits;
     int id = -1;
@@ -290,7 +293,7 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
         constexpr int NB = Shape::big_near + Shape::big_both;
         auto const take = [&](uint32_t k, int pos) {
             if constexpr(Shape::embed) {
-                best = min(best, (k & keep) | static_cast<uint32_t>(pos));
+                best = min(best, (k & (kKeepReg ? keep_reg : keep)) | static_cast<uint32_t>(pos));
             }
             else if(k < best) { // full-precision key: compare and select (two more half-rate ops per sphere)
                 best = k;
@@ -443,7 +446,7 @@ __device__ __forceinline__ bool shade_common(PathF32& p, bool hit, float t, int 
     p.oy = hy;
     p.oz = hz;
     p.last = id;
-    refl = __float_as_int(sb.w);
+    refl = __float_as_int(sb.w) & 0xff; // bit 8 flags an emitter (ptb_mega_sorted.cuh)
     return true;
 }
 

@@ -98,7 +98,7 @@ __device__ __forceinline__ bool bounce_smallpt(PathF32& p, bool hit, float t, in
             p.oy = hy;
             p.oz = hz;
             p.last = id;
-            int const refl = __float_as_int(sb.w);
+            int const refl = __float_as_int(sb.w) & 0xff;
             float const dn = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));
             if(refl == 1) { // SPEC :196-198
                 if(kCount) {

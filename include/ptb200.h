@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2
 
 #define PTB_SPHERE_BYTES 88
 #define PTB_CAMERA_BYTES 176
@@ -56,6 +56,9 @@ enum
     /* integrator variant */
     PTB_VARIANT_MEGAKERNEL = 0x0, /* one persistent kernel, path regeneration in place */
     PTB_VARIANT_WAVEFRONT = 0x1,  /* queue-based: generate / intersect / shade-by-material */
+    PTB_VARIANT_MEGAKERNEL_SORTED = 0x2, /* one persistent kernel; every warp sorts its paths by material through
+                                            shared-memory rings so that diffuse_ray / dielectric_ray run on full warps
+                                            (PTB_INTEGRATOR_PT only) */
     PTB_VARIANT_MASK = 0xF,
     /* arithmetic */
     PTB_PRECISION_FP32 = 0x00, /* throughput mode (the measured mode) */

@@ -186,6 +186,43 @@ def test_wavefront_variant_matches_megakernel(gpu, oracle_port, name):
     assert np.abs(img - ref).mean() < 2e-3
 
 
+@pytest.mark.parametrize("name", SCENES + ("spheres10k",))
+def test_sorted_megakernel_matches_megakernel(gpu, name):
+    """PTB_VARIANT_MEGAKERNEL_SORTED (shared-memory material sorting) traces the very same paths as the in-place
+    megakernel: same arithmetic, same uniforms; only the order of the float additions into a slot differs."""
+    W, H, S = (192, 108, 12) if name != "spheres10k" else (64, 36, 3)
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(23, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL)
+        mega = r.download_accum()
+        st_m = r.stats()
+        r.clear()
+        r.render(23, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
+        srt = r.download_accum()
+        st_s = r.stats()
+    assert np.all(mega[:, 3] == S) and np.all(srt[:, 3] == S)
+    assert st_s.paths == st_m.paths
+    assert (st_s.rays, st_s.hits_diffuse, st_s.hits_specular, st_s.hits_dielectric) == \
+        (st_m.rays, st_m.hits_diffuse, st_m.hits_specular, st_m.hits_dielectric)
+    assert np.isclose(mega[:, :3], srt[:, :3], rtol=1e-5, atol=1e-5).all(axis=1).mean() > 0.9999
+
+
+def test_sorted_megakernel_small_and_progressive(gpu):
+    W, H = 9, 7  # a single warp's worth of slots: the drain phase of the rings is most of the run
+    sph, cfg = gpu.builtin_scene("box", W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(3, 0, 2, gpu.VARIANT_MEGAKERNEL_SORTED)
+        r.render(3, 2, 3, gpu.VARIANT_MEGAKERNEL_SORTED)
+        a = r.download_accum()
+        r.clear()
+        r.render(3, 0, 5, gpu.VARIANT_MEGAKERNEL)
+        b = r.download_accum()
+    assert np.all(a[:, 3] == 5) and np.all(b[:, 3] == 5)
+    assert np.isclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-5).all()
+
+
 def test_wavefront_small_and_progressive(gpu):
     W, H = 9, 7  # fewer items than one block of the pool
     sph, cfg = gpu.builtin_scene("box", W, H)
