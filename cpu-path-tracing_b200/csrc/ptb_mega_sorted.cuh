@@ -11,63 +11,64 @@
 // states in shared memory:
 //
 //   READY  rays waiting for a closest-hit query (fresh camera samples and scattered paths)
-//   PARK   paths whose hit needs diffuse_ray / dielectric_ray
+//   PARK   paths whose hit needs work that only a few lanes would do
 //
 // Per loop iteration every lane holds one ray in registers: scan (all lanes), the part of the
-// bounce that is the same for all materials (hit record, emission, Russian roulette), then
+// bounce that is the same for every hit (hit point, emission, Russian roulette, throughput), then
 //   - a hit on the scene's DOMINANT material (template parameter kInline: mirror in box_mirror --
 //     80 % of the bounces -- diffuse in the plain box; chosen by the host from the previous
 //     launch's counters) scatters in place,
-//   - any other surviving hit is PARKED (four 16-byte shared stores) and the lane takes the
-//     next READY ray,
-//   - when 32 paths are parked the whole warp scatters them at once -- one entry per lane,
-//     all lanes busy -- and appends them to READY.
+//   - any other surviving hit -- another material, or the last allowed depth -- is PARKED
+//     (four 16-byte shared stores),
+//   - lanes whose path ended or was parked take the next READY ray (four 16-byte loads),
+//   - when 32 paths are parked the whole warp scatters them at once -- one entry per lane, all
+//     lanes busy: diffuse_ray / specular_ray / dielectric_ray -- and appends the survivors to READY.
 // Camera samples are generated 32 at a time into READY as before.  The random stream is keyed
 // by (seed, slot, sample) and travels with the path, so the image does not depend on any of this.
 //
-// Emission leaves the path state: a hit on an emitting sphere adds throughput * emission to the
-// slot straight away (red.global.add.v4.f32 with weight 0) and the path's end adds the weight 1,
-// so a parked path is 14 words -- four float4 planes.
+// Emission leaves the path state: it is added to the slot where it is picked up
+// (red.global.add.v4.f32 with weight 0) and the path's end adds the weight 1, so a parked
+// path is 14 words -- four float4 planes.
 //
 // Ring accounting (all warp-uniform): tokens = lanes + READY + PARK.  Camera samples are only
-// generated when READY + PARK <= 32, so tokens <= 96.  Loop order: refill, pop, scatter stage
-// (whenever PARK >= 32), bounce.  With 64-entry rings neither ring can overflow: see the scatter stage.
+// generated when READY + PARK <= 32, so tokens <= 96.  At the top of the loop either every lane
+// holds a ray -- then PARK >= 32 implies READY <= 32, room for the scatter stage's 32 results --
+// or READY is empty.  The scatter stage leaves PARK < 32, so the bounce may park all 32 lanes.
 #pragma once
 
 namespace ptb {
 
 constexpr int kSortedThreads = 128;
 constexpr int kSortedBlocksPerSm = 6;
-constexpr int kSortedRing = 64; // entries per ring, power of two
+constexpr int kSortedRing = 64;     // entries per ring, power of two
 constexpr int kEmissiveBit = 0x100; // in ShadePlanes::b.w next to the reflection tag (ptb_api.cpp: pack_geometry)
 
-struct WarpPool
-{
-    // one path per entry, both rings:
-    //   a = origin xyz, len           b = direction xyz, slot
-    //   c = throughput rgb, last      d = rng.state, rng.inc, depth | material << 8, -
-    float4 ra[kSortedRing], rb[kSortedRing], rc[kSortedRing], rd[kSortedRing];
-    float4 pa[kSortedRing], pb[kSortedRing], pc[kSortedRing], pd[kSortedRing];
-};
+// Byte layout of one warp's pool: two rings x four planes of float4[kSortedRing]
+//   plane a = origin xyz, len           plane b = direction xyz, slot
+//   plane c = throughput rgb, last      plane d = rng.state, rng.inc, depth | material << 8, -
+constexpr uint32_t kPlaneBytes = kSortedRing * 16u;
+constexpr uint32_t kRingBytes = 4u * kPlaneBytes;
+constexpr uint32_t kPoolBytes = 2u * kRingBytes;  // READY at +0, PARK at +kRingBytes
+constexpr uint32_t kRingMask = kPlaneBytes - 16u; // byte offset of an entry inside a plane, wraps
 
-// the four shading planes as one array: plane k of sphere i = base[k * stride + i]
-template<bool kSmem>
-struct ShadeArray
+// Explicit shared-window accesses: a 32-bit address register + immediate plane offset per access
+// (through generic pointers the compiler re-derives the window base in every loop iteration).
+__device__ __forceinline__ float4 lds128(uint32_t addr)
 {
-    float4 const* base;
-    int stride_rt;
-    __device__ __forceinline__ float4 get(int plane, int id) const
-    {
-        return base[plane * (kSmem ? kSmemShadeSpheres : stride_rt) + id];
-    }
-};
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 
 template<class Shape, bool kSmemShade, int kInline>
 __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorted_kernel(RenderParamsF32 const prm)
 {
-    __shared__ float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
-    __shared__ WarpPool s_pool[kSortedThreads / 32];
-    ShadeArray<kSmemShade> sh{ prm.shade.a, prm.n_total }; // the global planes are contiguous (ptb_api.cpp: shade_planes)
+    __shared__ __align__(16) float4 s_shade[kSmemShade ? 4 * kSmemShadeSpheres : 1];
+    __shared__ __align__(16) unsigned char s_pool[(kSortedThreads / 32) * kPoolBytes];
     if constexpr(kSmemShade) {
         for(int i = threadIdx.x; i < prm.n_total; i += kSortedThreads) {
             s_shade[i] = prm.shade.a[i];
@@ -76,18 +77,30 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
             s_shade[3 * kSmemShadeSpheres + i] = prm.shade.d[i];
         }
         __syncthreads();
-        sh.base = s_shade;
     }
+    // shading plane k of sphere i: shared window byte address shade_base + (k * stride + i) * 16, or the global array
+    uint32_t const shade_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_shade));
+    constexpr uint32_t kShadePlane = kSmemShadeSpheres * 16u;
+    float4 const* const gshade = prm.shade.a; // the global planes are contiguous (ptb_api.cpp: shade_planes)
+    int const gstride = prm.n_total;
+    auto const shade = [&](int plane, int id) -> float4 {
+        if constexpr(kSmemShade) {
+            return lds128(shade_base + static_cast<uint32_t>(plane) * kShadePlane + static_cast<uint32_t>(id) * 16u);
+        }
+        else {
+            return gshade[plane * gstride + id];
+        }
+    };
 
     constexpr uint32_t kFull = 0xffffffffu;
-    constexpr uint32_t kWrap = kSortedRing - 1;
     uint32_t const lane = threadIdx.x & 31u;
     uint32_t const lt_mask = (1u << lane) - 1u;
-    WarpPool& pool = s_pool[threadIdx.x >> 5];
+    uint32_t const ready_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pool)) + (threadIdx.x >> 5) * kPoolBytes;
+    uint32_t const park_base = ready_base + kRingBytes;
     float const k_uniform = Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f;
     uint32_t const keep_reg = prm.key_mask; // see closest_hit: a run-time value so that it stays in a register
 
-    // warp-uniform state
+    // warp-uniform state; ring positions are BYTE offsets inside a plane (multiples of 16, wrapped with kRingMask)
     uint32_t tile_sample0 = 0, tile_samples = 0, next_sample = 0;
     uint32_t ready_head = 0, ready_tail = 0, ready_count = 0;
     uint32_t park_head = 0, park_tail = 0, park_count = 0;
@@ -107,156 +120,171 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     p.last = -1;
     BounceCounters cnt{ 0, 0, 0, 0 };
 
+    // lanes of `need` take the oldest READY entries, lowest lane first; returns the new "holds a ray" mask
+    auto const pop = [&](uint32_t need) -> uint32_t {
+        uint32_t const rank = __popc(need & lt_mask);
+        bool const take = ((need >> lane) & 1u) != 0u && rank < ready_count;
+        if(take) {
+            uint32_t const rd = ready_base + ((ready_tail + rank * 16u) & kRingMask);
+            float4 const ea = lds128(rd);
+            float4 const eb = lds128(rd + kPlaneBytes);
+            float4 const ec = lds128(rd + 2u * kPlaneBytes);
+            float4 const ed = lds128(rd + 3u * kPlaneBytes);
+            p.ox = ea.x;
+            p.oy = ea.y;
+            p.oz = ea.z;
+            p.len = ea.w;
+            p.dx = eb.x;
+            p.dy = eb.y;
+            p.dz = eb.z;
+            slot = __float_as_uint(eb.w);
+            p.tr = ec.x;
+            p.tg = ec.y;
+            p.tb = ec.z;
+            p.last = __float_as_int(ec.w);
+            p.rng.state = __float_as_uint(ed.x);
+            p.rng.inc = __float_as_uint(ed.y);
+            p.depth = __float_as_int(ed.z);
+        }
+        uint32_t const wanted = static_cast<uint32_t>(__popc(need));
+        uint32_t const taken = min(wanted, ready_count);
+        ready_tail = (ready_tail + taken * 16u) & kRingMask;
+        ready_count -= taken;
+        return taken == wanted ? kFull : (~need | __ballot_sync(kFull, take));
+    };
+
     for(;;) {
-        // ---- refill: one camera sample per lane (main.cpp:186-190, camera.cpp:19-38) -----------------
-        if(!exhausted && ready_count + park_count <= 32u) {
-            __syncwarp(); // ring entries read by earlier pops are about to be overwritten
-            if(next_sample >= tile_samples) {
-                unsigned long long t = 0;
-                if(lane == 0) {
-                    t = atomicAdd(&prm.counters->tile_cursor, 1ull);
-                }
-                t = __shfl_sync(kFull, t, 0);
-                if(t >= prm.ntiles) {
-                    exhausted = true;
-                }
-                else {
-                    uint32_t const tile = static_cast<uint32_t>(t);
-                    uint32_t const group = tile / prm.nchunks;
-                    uint32_t const chunk = tile - group * prm.nchunks;
-                    tile_sample0 = chunk * prm.chunk;
-                    tile_samples = min(prm.chunk, prm.samples - tile_sample0);
-                    next_sample = 0;
-                    gen_slot = group * 32u + lane;
-                    gen_valid = min(32u, prm.nslots - group * 32u); // the slots of a tile are a prefix of its lanes
-                    if(lane < gen_valid) {
-                        slot_coords(gen_slot, prm.width, prm.ns, gen_x, gen_y, gen_sx, gen_sy);
+        // ================= slow path: ring maintenance, a few percent of the iterations ===========================
+        if(am != kFull || park_count >= 32u || (!exhausted && ready_count + park_count <= 32u)) {
+            // ---- scatter stage: up to 32 parked paths, one per lane -------------------------------------------
+            if(park_count >= 32u || (am != kFull && exhausted && ready_count == 0u && park_count != 0u)) {
+                __syncwarp(); // the parked entries were written by other lanes
+                uint32_t const k = min(32u, park_count);
+                bool out = false;
+                PathF32 q;
+                q.ox = q.oy = q.oz = q.dx = q.dy = q.dz = q.len = 0.0f;
+                q.rng.state = q.rng.inc = 0u;
+                float4 eb = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ec = eb;
+                int depth1 = 0;
+                if(lane < k) {
+                    uint32_t const rd = park_base + ((park_tail + lane * 16u) & kRingMask);
+                    float4 const ea = lds128(rd);
+                    eb = lds128(rd + kPlaneBytes);
+                    ec = lds128(rd + 2u * kPlaneBytes);
+                    float4 const ed = lds128(rd + 3u * kPlaneBytes);
+                    q.ox = ea.x;
+                    q.oy = ea.y;
+                    q.oz = ea.z;
+                    q.len = ea.w;
+                    q.dx = eb.x;
+                    q.dy = eb.y;
+                    q.dz = eb.z;
+                    q.rng.state = __float_as_uint(ed.x);
+                    q.rng.inc = __float_as_uint(ed.y);
+                    int const last = __float_as_int(ec.w);
+                    int const dm = __float_as_int(ed.z);
+                    int const mat = dm >> 8;
+                    depth1 = (dm & 0xff) + 1; // main.cpp:111 ++depth
+                    // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6)
+                    float4 const sa = shade(0, last);
+                    float const nx = fmaf(q.ox, sa.w, sa.x);
+                    float const ny = fmaf(q.oy, sa.w, sa.y);
+                    float const nz = fmaf(q.oz, sa.w, sa.z);
+                    float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
+                    if(mat == 0) {
+                        cnt.diffuse++;
+                        bool const front = dn < 0.0f; // hit_record.cpp:7
+                        scatter_diffuse(q, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
+                    }
+                    else if(mat == 1) {
+                        cnt.specular++;
+                        reflect_ray(q, nx, ny, nz);
+                    }
+                    else {
+                        cnt.dielectric++;
+                        scatter_dielectric(q, nx, ny, nz, dn);
+                    }
+                    // the ray scattered by the last iteration is never traced (main.cpp:111): the path ends here
+                    out = depth1 < kDepthLimit;
+                    if(!out) {
+                        red_add_v4(prm.accum + __float_as_uint(eb.w), 0.0f, 0.0f, 0.0f, 1.0f);
                     }
                 }
-            }
-            if(!exhausted) {
-                if(lane < gen_valid) {
-                    PathF32 g;
-                    g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
-                    gen_primary(g, c_scene.cam, gen_x, gen_y, gen_sx, gen_sy);
-                    uint32_t const w = (ready_head + lane) & kWrap;
-                    pool.ra[w] = make_float4(g.ox, g.oy, g.oz, g.len);
-                    pool.rb[w] = make_float4(g.dx, g.dy, g.dz, __uint_as_float(gen_slot));
-                    pool.rc[w] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
-                    pool.rd[w] = make_float4(__uint_as_float(g.rng.state), __uint_as_float(g.rng.inc), __int_as_float(0), 0.0f);
+                uint32_t const om = __ballot_sync(kFull, out);
+                if(out) {
+                    uint32_t const w = ready_base + ((ready_head + __popc(om & lt_mask) * 16u) & kRingMask);
+                    sts128(w, q.ox, q.oy, q.oz, q.len);
+                    sts128(w + kPlaneBytes, q.dx, q.dy, q.dz, eb.w);
+                    sts128(w + 2u * kPlaneBytes, ec.x, ec.y, ec.z, ec.w);
+                    sts128(w + 3u * kPlaneBytes, __uint_as_float(q.rng.state), __uint_as_float(q.rng.inc), __int_as_float(depth1), 0.0f);
                 }
-                ready_head = (ready_head + gen_valid) & kWrap;
-                ready_count += gen_valid;
-                next_sample += 1u;
+                uint32_t const nout = static_cast<uint32_t>(__popc(om));
+                park_tail = (park_tail + k * 16u) & kRingMask;
+                park_count -= k;
+                ready_head = (ready_head + nout * 16u) & kRingMask;
+                ready_count += nout;
                 __syncwarp();
             }
+
+            // ---- refill: one camera sample per lane (main.cpp:186-190, camera.cpp:19-38) -----------------
+            if(!exhausted && ready_count + park_count <= 32u) {
+                __syncwarp(); // ring entries read by earlier pops are about to be overwritten
+                if(next_sample >= tile_samples) {
+                    unsigned long long t = 0;
+                    if(lane == 0) {
+                        t = atomicAdd(&prm.counters->tile_cursor, 1ull);
+                    }
+                    t = __shfl_sync(kFull, t, 0);
+                    if(t >= prm.ntiles) {
+                        exhausted = true;
+                    }
+                    else {
+                        uint32_t const tile = static_cast<uint32_t>(t);
+                        uint32_t const group = tile / prm.nchunks;
+                        uint32_t const chunk = tile - group * prm.nchunks;
+                        tile_sample0 = chunk * prm.chunk;
+                        tile_samples = min(prm.chunk, prm.samples - tile_sample0);
+                        next_sample = 0;
+                        gen_slot = group * 32u + lane;
+                        gen_valid = min(32u, prm.nslots - group * 32u); // the slots of a tile are a prefix of its lanes
+                        if(lane < gen_valid) {
+                            slot_coords(gen_slot, prm.width, prm.ns, gen_x, gen_y, gen_sx, gen_sy);
+                        }
+                    }
+                }
+                if(!exhausted) {
+                    if(lane < gen_valid) {
+                        PathF32 g;
+                        g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
+                        gen_primary(g, c_scene.cam, gen_x, gen_y, gen_sx, gen_sy);
+                        uint32_t const w = ready_base + ((ready_head + lane * 16u) & kRingMask);
+                        sts128(w, g.ox, g.oy, g.oz, g.len);
+                        sts128(w + kPlaneBytes, g.dx, g.dy, g.dz, __uint_as_float(gen_slot));
+                        sts128(w + 2u * kPlaneBytes, 1.0f, 1.0f, 1.0f, __int_as_float(-1));
+                        sts128(w + 3u * kPlaneBytes, __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc), __int_as_float(0), 0.0f);
+                    }
+                    ready_head = (ready_head + gen_valid * 16u) & kRingMask;
+                    ready_count += gen_valid;
+                    next_sample += 1u;
+                    __syncwarp();
+                }
+            }
+
+            // ---- lanes that found READY empty at the end of their last bounce try again ---------------------
+            if(am != kFull && ready_count != 0u) {
+                am = pop(~am);
+            }
+            if(am == 0u) {
+                if(exhausted && ready_count == 0u && park_count == 0u) {
+                    break;
+                }
+                continue;
+            }
         }
 
-        // ---- lanes without a ray take the oldest READY entries ----------------------------------
-        uint32_t const need = ~am;
-        if(need != 0u && ready_count != 0u) {
-            uint32_t const rank = __popc(need & lt_mask);
-            bool const take = ((need >> lane) & 1u) != 0u && rank < ready_count;
-            if(take) {
-                uint32_t const rd = (ready_tail + rank) & kWrap;
-                float4 const ea = pool.ra[rd];
-                float4 const eb = pool.rb[rd];
-                float4 const ec = pool.rc[rd];
-                float4 const ed = pool.rd[rd];
-                p.ox = ea.x;
-                p.oy = ea.y;
-                p.oz = ea.z;
-                p.len = ea.w;
-                p.dx = eb.x;
-                p.dy = eb.y;
-                p.dz = eb.z;
-                slot = __float_as_uint(eb.w);
-                p.tr = ec.x;
-                p.tg = ec.y;
-                p.tb = ec.z;
-                p.last = __float_as_int(ec.w);
-                p.rng.state = __float_as_uint(ed.x);
-                p.rng.inc = __float_as_uint(ed.y);
-                p.depth = __float_as_int(ed.z);
-            }
-            uint32_t const wanted = static_cast<uint32_t>(__popc(need));
-            uint32_t const taken = min(wanted, ready_count);
-            ready_tail = (ready_tail + taken) & kWrap;
-            ready_count -= taken;
-            am = taken == wanted ? kFull : (am | __ballot_sync(kFull, take));
-        }
-
-        // ---- scatter stage: diffuse_ray / dielectric_ray for up to 32 parked paths, one per lane ----
-        // Runs AFTER the pop: with every lane holding a ray, tokens <= 96 gives READY <= 32 whenever PARK >= 32
-        // (room for the 32 results), and a lane still without a ray means READY is empty.  It leaves PARK < 32,
-        // so the bounce below may park all 32 lanes.
-        if(park_count >= 32u || (am != kFull && exhausted && ready_count == 0u && park_count != 0u)) {
-            __syncwarp(); // the parked entries were written by other lanes
-            uint32_t const k = min(32u, park_count);
-            if(lane < k) {
-                uint32_t const rd = (park_tail + lane) & kWrap;
-                float4 const ea = pool.pa[rd];
-                float4 const eb = pool.pb[rd];
-                float4 const ec = pool.pc[rd];
-                float4 const ed = pool.pd[rd];
-                PathF32 q;
-                q.ox = ea.x;
-                q.oy = ea.y;
-                q.oz = ea.z;
-                q.len = ea.w;
-                q.dx = eb.x;
-                q.dy = eb.y;
-                q.dz = eb.z;
-                q.rng.state = __float_as_uint(ed.x);
-                q.rng.inc = __float_as_uint(ed.y);
-                int const last = __float_as_int(ec.w);
-                int const dm = __float_as_int(ed.z);
-                // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6)
-                float4 const sa = sh.get(0, last);
-                float const nx = fmaf(q.ox, sa.w, sa.x);
-                float const ny = fmaf(q.oy, sa.w, sa.y);
-                float const nz = fmaf(q.oz, sa.w, sa.z);
-                float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
-                int const mat = dm >> 8;
-                if(mat == 0) {
-                    cnt.diffuse++;
-                    bool const front = dn < 0.0f; // hit_record.cpp:7
-                    scatter_diffuse(q, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
-                }
-                else if(mat == 1) {
-                    cnt.specular++;
-                    reflect_ray(q, nx, ny, nz);
-                }
-                else {
-                    cnt.dielectric++;
-                    scatter_dielectric(q, nx, ny, nz, dn);
-                }
-                uint32_t const w = (ready_head + lane) & kWrap;
-                pool.ra[w] = make_float4(q.ox, q.oy, q.oz, q.len);
-                pool.rb[w] = make_float4(q.dx, q.dy, q.dz, eb.w);
-                pool.rc[w] = ec;
-                pool.rd[w] = make_float4(__uint_as_float(q.rng.state), __uint_as_float(q.rng.inc),
-                                         __int_as_float((dm & 0xff) + 1), 0.0f); // main.cpp:111 ++depth
-            }
-            park_tail = (park_tail + k) & kWrap;
-            park_count -= k;
-            ready_head = (ready_head + k) & kWrap;
-            ready_count += k;
-            __syncwarp();
-            if(am != kFull) {
-                continue; // hand the fresh rays to the lanes that wait for one
-            }
-        }
-        if(am == 0u) {
-            if(exhausted && ready_count == 0u && park_count == 0u) {
-                break;
-            }
-            continue;
-        }
-
-        // ---- one bounce: main.cpp:111-155; the material branch runs here only for material kInline ----------
-        bool park = false;
-        bool alive = ((am >> lane) & 1u) != 0u;
+        // ================= one bounce: main.cpp:111-155 =========================================================
+        bool park = false, ended = false;
+        bool const alive = ((am >> lane) & 1u) != 0u;
         int material = 0;
         if(alive) {
             RayTerms const r = ray_terms(p, k_uniform);
@@ -264,56 +292,39 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
             int id;
             bool const hit = closest_hit<Shape, true>(c_scene, prm.geo, p, r, t, id, keep_reg);
             cnt.rays++;
-            float fr = 0.0f, fg = 0.0f, fb = 0.0f; // radiance picked up by this bounce
-            bool flush = false, ended = false;
-            float4 sa = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if(!hit) {
-                // main.cpp:116-119 sky gradient on the unit direction
+                // main.cpp:116-119 sky gradient on the unit direction; the path ends
                 float const tt = 0.5f * (p.dy + 1.0f);
                 float const omt = 1.0f - tt;
-                fr = p.tr * fmaf(0.5f, tt, omt);
-                fg = p.tg * fmaf(0.7f, tt, omt);
-                fb = p.tb * (omt + tt);
+                red_add_v4(prm.accum + slot, p.tr * fmaf(0.5f, tt, omt), p.tg * fmaf(0.7f, tt, omt), p.tb * (omt + tt), 1.0f);
                 ended = true;
             }
             else {
-                sa = sh.get(0, id);
-                float4 const sb = sh.get(1, id);
-                int const tag = __float_as_int(sb.w);
-                material = tag & 0xff;
                 // hit_record.cpp:5-6
                 p.ox = fmaf(p.dx, t, p.ox);
                 p.oy = fmaf(p.dy, t, p.oy);
                 p.oz = fmaf(p.dz, t, p.oz);
                 p.last = id;
+                float4 const sb = shade(1, id);
+                int const tag = __float_as_int(sb.w);
+                material = tag & 0xff;
                 if((tag & kEmissiveBit) != 0) { // main.cpp:126
-                    fr = p.tr * sb.x;
-                    fg = p.tg * sb.y;
-                    fb = p.tb * sb.z;
-                    flush = true;
+                    red_add_v4(prm.accum + slot, p.tr * sb.x, p.tg * sb.y, p.tb * sb.z, 0.0f);
                 }
                 // main.cpp:128-139 Russian roulette: p = max(color), survivor weight color / p
                 bool const roulette = p.depth > kRouletteThreshold;
-                float4 const col = sh.get(roulette ? 3 : 2, id);
+                float4 const col = shade(roulette ? 3 : 2, id);
                 if(roulette) {
                     ended = !(rng_uniform_f32(p.rng) < col.w);
                 }
                 p.tr *= col.x;
                 p.tg *= col.y;
                 p.tb *= col.z;
-                if(!ended && p.depth >= kDepthLimit - 1) {
-                    // the ray scattered by the last iteration is never traced (main.cpp:111): count the hit, stop
-                    cnt.diffuse += material == 0 ? 1u : 0u;
-                    cnt.specular += material == 1 ? 1u : 0u;
-                    cnt.dielectric += material == 2 ? 1u : 0u;
-                    ended = true;
+                if(ended) {
+                    red_add_v4(prm.accum + slot, 0.0f, 0.0f, 0.0f, 1.0f);
                 }
-            }
-            if(flush || ended) {
-                red_add_v4(prm.accum + slot, fr, fg, fb, ended ? 1.0f : 0.0f);
-            }
-            if(!ended) {
-                if(material == kInline) {
+                else if(material == kInline && p.depth < kDepthLimit - 1) {
+                    float4 const sa = shade(0, id);
                     float const nx = fmaf(p.ox, sa.w, sa.x); // outward normal (P - c) / R, hit_record.cpp:6
                     float const ny = fmaf(p.oy, sa.w, sa.y);
                     float const nz = fmaf(p.oz, sa.w, sa.z);
@@ -329,27 +340,27 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     p.depth++;
                 }
                 else {
-                    park = true;
+                    park = true; // another material, or the last allowed depth (main.cpp:111)
                 }
             }
-            alive = !(ended || park);
         }
 
-        // ---- park what needs one of the other scatter functions ------------------------------------------
-        am = __ballot_sync(kFull, alive);
+        // ================= turnover: park, then hand a READY ray to every lane without one ========================
         uint32_t const pm = __ballot_sync(kFull, park);
-        if(pm != 0u) {
+        uint32_t const need = ~am | pm | __ballot_sync(kFull, ended);
+        if(need != 0u) {
             if(park) {
-                uint32_t const w = (park_head + __popc(pm & lt_mask)) & kWrap;
-                pool.pa[w] = make_float4(p.ox, p.oy, p.oz, p.len);
-                pool.pb[w] = make_float4(p.dx, p.dy, p.dz, __uint_as_float(slot));
-                pool.pc[w] = make_float4(p.tr, p.tg, p.tb, __int_as_float(p.last));
-                pool.pd[w] = make_float4(__uint_as_float(p.rng.state), __uint_as_float(p.rng.inc),
-                                         __int_as_float(p.depth | (material << 8)), 0.0f);
+                uint32_t const w = park_base + ((park_head + __popc(pm & lt_mask) * 16u) & kRingMask);
+                sts128(w, p.ox, p.oy, p.oz, p.len);
+                sts128(w + kPlaneBytes, p.dx, p.dy, p.dz, __uint_as_float(slot));
+                sts128(w + 2u * kPlaneBytes, p.tr, p.tg, p.tb, __int_as_float(p.last));
+                sts128(w + 3u * kPlaneBytes, __uint_as_float(p.rng.state), __uint_as_float(p.rng.inc),
+                       __int_as_float(p.depth | (material << 8)), 0.0f);
             }
-            uint32_t const n = __popc(pm);
-            park_head = (park_head + n) & kWrap;
+            uint32_t const n = static_cast<uint32_t>(__popc(pm));
+            park_head = (park_head + n * 16u) & kRingMask;
             park_count += n;
+            am = pop(need);
         }
     }
 
