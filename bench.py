@@ -204,7 +204,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--spp", type=int, default=0, help="override the config's total samples per pixel")
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "sorted"])
+    ap.add_argument("--variant", default="sorted", choices=["mega", "wavefront", "sorted"],
+                    help="sorted = material-sorted megakernel (the product path); mega = in-place megakernel; wavefront")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -238,7 +239,8 @@ def main():
     dr = DistributedRenderer(pkg, local, rank, world)
     if scene == "smallpt":
         spheres, cam = pkg.builtin_smallpt_scene()  # cam = cam8
-        flags |= pkg.INTEGRATOR_SMALLPT
+        args.variant = "mega"  # the sandbox integrator (splitting glass) runs on the in-place megakernel only
+        flags = pkg.PRECISION_FP32 | pkg.VARIANT_MEGAKERNEL | pkg.INTEGRATOR_SMALLPT
         dr.setup(spheres, None, width, height, 2, smallpt_camera=cam)
         set_camera = dr.renderer.set_smallpt_camera
     else:

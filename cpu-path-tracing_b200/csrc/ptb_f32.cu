@@ -394,12 +394,41 @@ __global__ void __launch_bounds__(kMegaThreads) probe_f32_kernel(ProbeParams con
 
     BounceCounters cnt{ 0, 0, 0, 0 };
     bool alive = true;
+#ifdef PTB_DEBUG_NAN
+    int bounce_index = 0; // development build (dev/build_variant.sh): report the first bounce that leaves a non-finite state
+#endif
     while(alive) {
         RayTerms const r = ray_terms(p, Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f);
         float t;
         int id;
         bool const hit = closest_hit<Shape>(c_scene, geo, p, r, t, id);
+#ifdef PTB_DEBUG_NAN
+        PathF32 const before = p;
+#endif
         alive = Integ::bounce(p, hit, t, id, sp, cnt, split);
+#ifdef PTB_DEBUG_NAN
+        float const chk = p.ox + p.oy + p.oz + p.dx + p.dy + p.dz + p.tr + p.tg + p.tb + p.er + p.eg + p.eb;
+        float const d2 = p.dx * p.dx + p.dy * p.dy + p.dz * p.dz;
+        if(!isfinite(chk) || (alive && fabsf(d2 - 1.0f) > 1e-3f)) {
+            q.radiance[3 * i + 0] = bounce_index;
+            q.radiance[3 * i + 1] = hit ? id : -1;
+            q.radiance[3 * i + 2] = t;
+            if(q.ray != nullptr) {
+                q.ray[6 * i + 0] = before.ox;
+                q.ray[6 * i + 1] = before.oy;
+                q.ray[6 * i + 2] = before.oz;
+                q.ray[6 * i + 3] = before.dx;
+                q.ray[6 * i + 4] = before.dy;
+                q.ray[6 * i + 5] = before.dz;
+                q.primary_hit[i] = __float_as_int(d2); // |d|^2 after the bounce
+            }
+            if(q.draws != nullptr) {
+                q.draws[i] = 1000u + static_cast<uint32_t>(before.last + 1);
+            }
+            return;
+        }
+        bounce_index++;
+#endif
     }
     q.radiance[3 * i + 0] = p.er;
     q.radiance[3 * i + 1] = p.eg;

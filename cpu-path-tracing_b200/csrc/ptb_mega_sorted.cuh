@@ -187,9 +187,8 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     depth1 = (dm & 0xff) + 1; // main.cpp:111 ++depth
                     // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6)
                     float4 const sa = shade(0, last);
-                    float const nx = fmaf(q.ox, sa.w, sa.x);
-                    float const ny = fmaf(q.oy, sa.w, sa.y);
-                    float const nz = fmaf(q.oz, sa.w, sa.z);
+                    float nx, ny, nz;
+                    unit_normal(q.ox, q.oy, q.oz, sa, nx, ny, nz);
                     float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
                     if(mat == 0) {
                         cnt.diffuse++;
@@ -325,9 +324,8 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 }
                 else if(material == kInline && p.depth < kDepthLimit - 1) {
                     float4 const sa = shade(0, id);
-                    float const nx = fmaf(p.ox, sa.w, sa.x); // outward normal (P - c) / R, hit_record.cpp:6
-                    float const ny = fmaf(p.oy, sa.w, sa.y);
-                    float const nz = fmaf(p.oz, sa.w, sa.z);
+                    float nx, ny, nz; // outward unit normal, hit_record.cpp:6
+                    unit_normal(p.ox, p.oy, p.oz, sa, nx, ny, nz);
                     if constexpr(kInline == 1) {
                         cnt.specular++;
                         reflect_ray(p, nx, ny, nz); // specular_ray, main.cpp:60-67

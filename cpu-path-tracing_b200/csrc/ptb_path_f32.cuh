@@ -378,15 +378,37 @@ struct BounceCounters
     uint32_t dielectric;
 };
 
+// hit_record.cpp:6 -- outward UNIT normal norm(P - centre); sa = (-c/R, 1/R).
+// (P - c) / R alone is unit only if P lies exactly on the sphere, and P = o + t d with t solved for |d| = 1: a
+// deviation delta of |d|^2 puts P off the surface by t delta / 2, the mirror formula with the resulting non-unit
+// normal multiplies delta by ~4 t / R (small sphere hit from afar) or ~17 (inside a glass ball, far root
+// 2 (c - o).d), and a chain of such bounces overflowed binary32 within ten bounces on the 10 001-sphere scene.
+// The reference normalises here too; with a unit normal the mirror formula preserves |d| and delta stays at
+// rounding level for the whole path.  MUFU.RSQ rather than a Newton step about 1: its error does not depend on
+// how far off the surface P is, so nothing feeds back.
+__device__ __forceinline__ void unit_normal(float px, float py, float pz, float4 const& sa, float& nx, float& ny, float& nz)
+{
+    nx = fmaf(px, sa.w, sa.x);
+    ny = fmaf(py, sa.w, sa.y);
+    nz = fmaf(pz, sa.w, sa.z);
+    float const inv = fast_rsqrt(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+    nx *= inv;
+    ny *= inv;
+    nz *= inv;
+}
+
 // specular_ray, main.cpp:60-67: mirror about the OUTWARD normal; the length of the
 // reference's direction is unchanged by it (p.len stays).  The reference then draws one
 // uniform and multiplies it by fuzziness = 0 -- the draw must still advance the stream.
 __device__ __forceinline__ void reflect_ray(PathF32& p, float nx, float ny, float nz)
 {
     float const dn2 = 2.0f * fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));
-    p.dx = fmaf(-dn2, nx, p.dx);
-    p.dy = fmaf(-dn2, ny, p.dy);
-    p.dz = fmaf(-dn2, nz, p.dz);
+    float const rx = fmaf(-dn2, nx, p.dx);
+    float const ry = fmaf(-dn2, ny, p.dy);
+    float const rz = fmaf(-dn2, nz, p.dz);
+    p.dx = rx;
+    p.dy = ry;
+    p.dz = rz;
     (void)rng_next32(p.rng);
 }
 
@@ -417,9 +439,7 @@ __device__ __forceinline__ bool shade_common(PathF32& p, bool hit, float t, int 
     float const hx = fmaf(p.dx, t, p.ox);
     float const hy = fmaf(p.dy, t, p.oy);
     float const hz = fmaf(p.dz, t, p.oz);
-    nx = fmaf(hx, sa.w, sa.x); // outward normal (P - c)/R
-    ny = fmaf(hy, sa.w, sa.y);
-    nz = fmaf(hz, sa.w, sa.z);
+    unit_normal(hx, hy, hz, sa, nx, ny, nz);
 
     // main.cpp:126
     p.er = fmaf(p.tr, sb.x, p.er);

@@ -73,9 +73,8 @@ __device__ __forceinline__ bool bounce_smallpt(PathF32& p, bool hit, float t, in
         float const hx = fmaf(p.dx, t, p.ox);
         float const hy = fmaf(p.dy, t, p.oy);
         float const hz = fmaf(p.dz, t, p.oz);
-        float const nx = fmaf(hx, sa.w, sa.x); // n = (x - p) / R, outward
-        float const ny = fmaf(hy, sa.w, sa.y);
-        float const nz = fmaf(hz, sa.w, sa.z);
+        float nx, ny, nz; // n = norm(x - p), outward (sandbox/main.cpp:160)
+        unit_normal(hx, hy, hz, sa, nx, ny, nz);
         // every visited hit contributes W * e, whether the roulette then kills the path (it returns
         // obj.e) or not (obj.e + f * child)
         p.er = fmaf(p.tr, sb.x, p.er);

@@ -38,7 +38,7 @@ auto main(int argc, char* argv[]) -> int
     int spp = 4;
     int device = 0;
     unsigned long long seed = 1;
-    unsigned flags = PTB_VARIANT_MEGAKERNEL | PTB_PRECISION_FP32;
+    unsigned flags = PTB_VARIANT_MEGAKERNEL_SORTED | PTB_PRECISION_FP32;
     std::string scene_name{ "box_mirror" };
     std::string out{ "image.ppm" };
 

@@ -22,6 +22,9 @@ print(name, "counts ok:", bool(np.all(a[:, 3] == S)), bool(np.all(b[:, 3] == S))
       "sum n:", a[:, 3].sum(), b[:, 3].sum())
 for k in ("paths", "rays", "hits_diffuse", "hits_specular", "hits_dielectric"):
     print(f"  {k}: {getattr(sa, k)} {getattr(sb, k)}")
+print("  non-finite slots:", int((~np.isfinite(a)).any(axis=1).sum()), int((~np.isfinite(b)).any(axis=1).sum()))
+for i in np.nonzero((~np.isfinite(a)).any(axis=1))[0][:4]:
+    print("   non-finite slot", i, a[i], b[i])
 d = np.abs(a[:, :3] - b[:, :3])
 rel = d / np.maximum(np.abs(a[:, :3]), 1e-3)
 print("  max abs diff", d.max(), "max rel", rel.max(), "frac slots > 1e-5 rel:", (rel.max(axis=1) > 1e-5).mean(),

@@ -128,14 +128,15 @@ def test_fp32_samples_against_oracle(gpu, oracle_port, name):
     assert np.abs(z).max() < 4.0, f"FP32 mean radiance biased: z = {z}"
 
 
+@pytest.mark.parametrize("variant", ["VARIANT_MEGAKERNEL", "VARIANT_MEGAKERNEL_SORTED"])
 @pytest.mark.parametrize("name", SCENES)
-def test_fp32_image_against_oracle_same_seed(gpu, oracle_port, name):
+def test_fp32_image_against_oracle_same_seed(gpu, oracle_port, name, variant):
     W, H, S = 160, 90, 8
     sph, cfg = gpu.builtin_scene(name, W, H)
     cam = gpu.camera_with_config(cfg)
     ref = oracle_port.render(sph, cam, W, H, S, 2, 17, 0)
     with make_renderer(gpu, sph, cam, W, H) as r:
-        r.render(17, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL)
+        r.render(17, 0, S, gpu.PRECISION_FP32 | getattr(gpu, variant))
         img = r.resolve()
         st = r.stats()
         acc = r.download_accum()
@@ -155,7 +156,7 @@ def test_fp32_image_rmse_within_monte_carlo_noise(gpu, oracle_port):
     refs = np.stack([oracle_port.render(sph, cam, W, H, S, 2, 1000 + k, 0) for k in range(K)])
     mean_ref, var_px = refs.mean(axis=0), refs.var(axis=0, ddof=1)
     with make_renderer(gpu, sph, cam, W, H) as r:
-        r.render(4242, 0, S, gpu.PRECISION_FP32)
+        r.render(4242, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
         img = r.resolve()
     for c in range(3):
         rmse = np.sqrt(np.mean((img[..., c] - mean_ref[..., c]) ** 2))
@@ -202,6 +203,7 @@ def test_sorted_megakernel_matches_megakernel(gpu, name):
         srt = r.download_accum()
         st_s = r.stats()
     assert np.all(mega[:, 3] == S) and np.all(srt[:, 3] == S)
+    assert np.isfinite(mega).all() and np.isfinite(srt).all()
     assert st_s.paths == st_m.paths
     assert (st_s.rays, st_s.hits_diffuse, st_s.hits_specular, st_s.hits_dielectric) == \
         (st_m.rays, st_m.hits_diffuse, st_m.hits_specular, st_m.hits_dielectric)
