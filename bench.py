@@ -365,6 +365,14 @@ def main():
                 "peak_source": "FFMA loop measured live on this GPU (ptb_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.45",
             },
         }
+        if scene == "spheres10k":
+            # flop_per_path is the REFERENCE's algorithm (a 10 001-sphere linear scan per ray);
+            # the kernel answers the same queries through a bounding-volume hierarchy (~9 box pairs + ~2.4 sphere tests
+            # per ray), so "achieved" is an equivalent-work rate and may exceed the hardware peak -- not a pipe fraction
+            line["roofline"]["frac"] = None
+            line["roofline"]["equivalent_scan_frac"] = achieved / peak_tflops
+            line["roofline"]["note"] = ("closest hit through a hierarchy (PTB_ACCEL_AUTO): algorithmic flops are the reference's "
+                                        "linear scan, achieved/peak > 1 means work skipped, not a pipe utilisation")
         if not args.no_cpu_baseline:
             bw, bh = (width, height) if scene != "spheres10k" else (width // 8, height // 8)
             bs = 4 if scene != "spheres10k" else 1

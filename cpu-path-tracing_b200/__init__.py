@@ -34,6 +34,8 @@ CAMERA_CONFIG_BYTES = 112
 VARIANT_MEGAKERNEL = 0x0
 VARIANT_WAVEFRONT = 0x1
 VARIANT_MEGAKERNEL_SORTED = 0x2
+ACCEL_AUTO = 0x0000
+ACCEL_SCAN = 0x1000
 PRECISION_FP32 = 0x00
 PRECISION_FP64 = 0x10
 INTEGRATOR_PT = 0x000

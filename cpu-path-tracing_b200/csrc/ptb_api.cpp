@@ -5,6 +5,7 @@
 // There is deliberately no CPU path in this file: every compute entry point needs a
 // live context, and ptb_create fails when no CUDA device is usable.
 #include "../../include/ptb200.h"
+#include "ptb_bvh.hpp"
 #include "ptb_kernels.h"
 #include "ptb_rng.cuh"
 
@@ -45,6 +46,14 @@ struct ptb_context
     int* d_order = nullptr;
     float4* d_shade = nullptr; // 4 planes of n
     size_t geo_cap = 0;
+    // bounding-volume hierarchy over the small spheres (ptb_bvh.hpp); built when they do not fit the constant lists
+    float4* d_bvh_nodes = nullptr;
+    SmallGeo* d_bvh_geo = nullptr;
+    int* d_bvh_pos = nullptr;
+    size_t bvh_node_cap = 0, bvh_leaf_cap = 0;
+    int bvh_root = 0;
+    bool have_bvh = false;
+    int bvh_depth = 0, bvh_node_count = 0;
 
     // image
     int width = 0, height = 0, ns = 0;
@@ -169,12 +178,17 @@ struct PackedScene
     std::vector<int> order;          // list position -> original index
     std::vector<float4> shade;       // 4 planes, by list position
     SceneCounts counts{};
+    BvhTree bvh;                     // over the small spheres, leaf_order in LIST POSITIONS (empty: not built)
+    std::vector<SmallGeo> bvh_geo;   // leaf order
+    std::vector<int> bvh_pos;        // leaf slot -> list position | both-roots flag
 };
 
 // A sphere can only ever be hit at its NEAR root when no ray origin can lie inside it:
 // it must be opaque (diffuse / specular scatter back to the outside, main.cpp:44-67) and the
 // camera lens (position +- the largest lens offset, camera.cpp:34-35: |rd*(s+t)| <= 2*sqrt(2)*lens_radius)
 // must be outside it.  Dielectric spheres are traversed from inside and keep both roots.
+// Overlapping spheres (BASELINE config 5 is full of them) change nothing: a hit point on one sphere that lay inside
+// an opaque neighbour would have been hidden by that neighbour, so no ray ever STARTS inside an opaque sphere.
 bool near_root_only(RawSphere const& s, ptb_context const* ctx)
 {
     if(s.reflection == 2 || (!ctx->have_camera && !ctx->have_sbcam)) {
@@ -217,6 +231,18 @@ PackedScene pack_geometry(ptb_context* ctx)
     std::vector<int> big_near[4]; // x, y, z, other
     double k_first = 0.0;
     bool uniform_k = true, any_big = false;
+
+    // tree over the ordinary-sized spheres, in the shifted FP32 frame the kernels use
+    std::vector<int> small_ids;
+    std::vector<BvhSphere> small_f32;
+    for(int i = 0; i < n; ++i) {
+        if(s[i].radius <= kBigRadius) {
+            small_ids.push_back(i);
+            small_f32.push_back(BvhSphere{ static_cast<float>(s[i].px - sh[0]), static_cast<float>(s[i].py - sh[1]),
+                                           static_cast<float>(s[i].pz - sh[2]), static_cast<float>(s[i].radius) });
+        }
+    }
+
     for(int i = 0; i < n; ++i) {
         bool const big = s[i].radius > kBigRadius;
         bool const near_only = near_root_only(s[i], ctx);
@@ -329,6 +355,23 @@ PackedScene pack_geometry(ptb_context* ctx)
         out.shade[2 * N + P] = c;
         out.shade[3 * N + P] = d;
     }
+
+    // Device hierarchy: only when the small spheres do not fit the constant lists (otherwise the unrolled or the
+    // constant-bank scan is faster than any traversal).  Leaves carry LIST POSITIONS.
+    int const n_small = out.counts.small_near + out.counts.small_both;
+    BvhTree small_tree = n_small > kMaxConstSpheres ? build_bvh(small_f32) : BvhTree{};
+    if(n_small > kMaxConstSpheres && small_tree.max_depth <= kBvhStack) {
+        std::vector<int> list_pos_of(static_cast<size_t>(n), -1); // original index -> list position
+        for(int pos = 0; pos < n; ++pos) {
+            list_pos_of[static_cast<size_t>(out.order[static_cast<size_t>(pos)])] = pos;
+        }
+        out.bvh = std::move(small_tree);
+        for(int j : out.bvh.leaf_order) { // j = index into small_ids
+            int const pos = list_pos_of[static_cast<size_t>(small_ids[static_cast<size_t>(j)])];
+            out.bvh_geo.push_back(out.small_geo[static_cast<size_t>(pos)]);
+            out.bvh_pos.push_back(pos | (pos >= out.counts.small_near ? static_cast<int>(0x80000000u) : 0));
+        }
+    }
     return out;
 }
 
@@ -439,6 +482,36 @@ int rebuild_device_scene(ptb_context* ctx)
         PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_shade, ps.shade.data(), 4 * static_cast<size_t>(n) * sizeof(float4),
                                       cudaMemcpyHostToDevice, st));
     }
+    ctx->have_bvh = !ps.bvh_geo.empty();
+    ctx->bvh_depth = ps.bvh.max_depth;
+    ctx->bvh_node_count = static_cast<int>(ps.bvh.nodes.size());
+    if(ctx->have_bvh) {
+        size_t const nn = std::max<size_t>(ps.bvh.nodes.size(), 1), nl = ps.bvh_geo.size();
+        if(nn > ctx->bvh_node_cap) {
+            cudaFree(ctx->d_bvh_nodes);
+            ctx->d_bvh_nodes = nullptr;
+            ctx->bvh_node_cap = 0;
+            PTB_CUDA(ctx, cudaMalloc(&ctx->d_bvh_nodes, nn * sizeof(BvhNode64)));
+            ctx->bvh_node_cap = nn;
+        }
+        if(nl > ctx->bvh_leaf_cap) {
+            cudaFree(ctx->d_bvh_geo);
+            cudaFree(ctx->d_bvh_pos);
+            ctx->d_bvh_geo = nullptr;
+            ctx->d_bvh_pos = nullptr;
+            ctx->bvh_leaf_cap = 0;
+            PTB_CUDA(ctx, cudaMalloc(&ctx->d_bvh_geo, nl * sizeof(SmallGeo)));
+            PTB_CUDA(ctx, cudaMalloc(&ctx->d_bvh_pos, nl * sizeof(int)));
+            ctx->bvh_leaf_cap = nl;
+        }
+        if(!ps.bvh.nodes.empty()) {
+            PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bvh_nodes, ps.bvh.nodes.data(), ps.bvh.nodes.size() * sizeof(BvhNode64),
+                                          cudaMemcpyHostToDevice, st));
+        }
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bvh_geo, ps.bvh_geo.data(), nl * sizeof(SmallGeo), cudaMemcpyHostToDevice, st));
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bvh_pos, ps.bvh_pos.data(), nl * sizeof(int), cudaMemcpyHostToDevice, st));
+        ctx->bvh_root = ps.bvh.root;
+    }
     PTB_CUDA(ctx, cudaStreamSynchronize(st)); // ps goes out of scope
     return PTB_OK;
 }
@@ -454,12 +527,18 @@ ShadePlanes shade_planes(ptb_context* ctx)
     return sp;
 }
 
-GeoLists geo_lists(ptb_context* ctx)
+GeoLists geo_lists(ptb_context* ctx, bool use_bvh = true)
 {
-    GeoLists g;
+    GeoLists g{};
     g.small_geo = ctx->d_small;
     g.big_geo = ctx->d_big;
     g.order = ctx->d_order;
+    if(use_bvh && ctx->have_bvh) {
+        g.bvh_nodes = ctx->d_bvh_nodes;
+        g.bvh_geo = ctx->d_bvh_geo;
+        g.bvh_pos = ctx->d_bvh_pos;
+        g.bvh_root = ctx->bvh_root;
+    }
     return g;
 }
 
@@ -566,6 +645,9 @@ void ptb_destroy(ptb_context* ctx)
     cudaFree(ctx->d_big);
     cudaFree(ctx->d_order);
     cudaFree(ctx->d_shade);
+    cudaFree(ctx->d_bvh_nodes);
+    cudaFree(ctx->d_bvh_geo);
+    cudaFree(ctx->d_bvh_pos);
     cudaFree(ctx->d_accum);
     cudaFree(ctx->d_accum64);
     cudaFree(ctx->d_rgb);
@@ -782,7 +864,9 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     uint32_t const variant = flags & PTB_VARIANT_MASK;
     uint32_t const precision = flags & PTB_PRECISION_MASK;
     uint32_t const integrator = flags & PTB_INTEGRATOR_MASK;
-    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK)) != 0 || variant > PTB_VARIANT_MEGAKERNEL_SORTED ||
+    uint32_t const accel = flags & PTB_ACCEL_MASK;
+    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK | PTB_ACCEL_MASK)) != 0 ||
+       variant > PTB_VARIANT_MEGAKERNEL_SORTED || (accel != PTB_ACCEL_AUTO && accel != PTB_ACCEL_SCAN) ||
        (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) ||
        (integrator != PTB_INTEGRATOR_PT && integrator != PTB_INTEGRATOR_SMALLPT)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
@@ -859,7 +943,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         p.accum = active_accum(ctx);
         p.counters = ctx->d_counters;
         p.shade = shade_planes(ctx);
-        p.geo = geo_lists(ctx);
+        p.geo = geo_lists(ctx, accel != PTB_ACCEL_SCAN);
         p.n_total = ctx->n;
         p.key_mask = ~((1u << 4) - 1u); // kIdBits of ptb_path_f32.cuh
         if(variant == PTB_VARIANT_WAVEFRONT) {
@@ -1188,7 +1272,7 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
     }
     else {
         PTB_CUDA_T(upload_const_scene(ctx->cs, st));
-        PTB_CUDA_T(launch_probe_f32(q, ctx->counts, shade_planes(ctx), geo_lists(ctx), st, smallpt));
+        PTB_CUDA_T(launch_probe_f32(q, ctx->counts, shade_planes(ctx), geo_lists(ctx, (flags & PTB_ACCEL_MASK) != PTB_ACCEL_SCAN), st, smallpt));
     }
     ctx->stats.kernel_launches += 1;
     PTB_CUDA_T(cudaMemcpyAsync(primary_hit_out, d_hit, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

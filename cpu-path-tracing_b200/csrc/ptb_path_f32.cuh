@@ -174,13 +174,29 @@ __device__ __forceinline__ RayTerms ray_terms(PathF32 const& p, float k_uniform 
 // 2*nb exactly; taking it from there instead of from nb +- sqrt(nb^2 - c) with c ~ 0 removes the
 // binary32 failure where a ray refracted OUT of a glass ball re-hits it from inside a few 1e-4 further
 // on, is totally reflected and then circles inside for ~1000 bounces (seen on the sandbox scene).
+// Discriminant of a small sphere for scenes that are LARGE against the sphere: half_b^2 - c with c = |c - o|^2 - r^2
+// subtracts two numbers of size |c - o|^2 to get one of size r^2 -- at 70 units from a r = 0.2 sphere binary32 leaves
+// an error of 1.5 % of the sphere's cross-section in the hit / miss decision.  r^2 - |(c - o) - ((c - o).d) d|^2, the
+// squared distance from the centre to the ray, has no such cancellation (unit d): two more FFMA.
+__device__ __forceinline__ float small_disc_far(float cx, float cy, float cz, float nb, float r2, PathF32 const& p)
+{
+    float const qx = fmaf(-nb, p.dx, cx), qy = fmaf(-nb, p.dy, cy), qz = fmaf(-nb, p.dz, cz);
+    return fmaf(-qx, qx, fmaf(-qy, qy, fmaf(-qz, qz, r2)));
+}
+
 template<bool kBoth, bool kRobust = false>
 __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& p, RayTerms const& r, bool self = false)
 {
     float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz; // c - o = -oc
     float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));       // -half_b
-    float const cc = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, -s.r2))); // c (sphere.cpp:11)
-    float const disc = fmaf(nb, nb, -cc);
+    float disc;
+    if constexpr(kRobust) {
+        disc = small_disc_far(cx, cy, cz, nb, s.r2, p);
+    }
+    else {
+        float const cc = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, -s.r2))); // c (sphere.cpp:11)
+        disc = fmaf(nb, nb, -cc);
+    }
     float const sq = disc_sqrt(disc);
     float const h = nb - r.eps;
     float const tn = h - sq;
@@ -247,6 +263,77 @@ __device__ __forceinline__ uint32_t key_big_axis(BigGeo const& b, PathF32 const&
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
     return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
+}
+
+// ---- closest hit through the bounding-volume hierarchy (ptb_bvh.hpp) -------------
+// Same answer as the linear scan of main.cpp:30-42 over the small spheres: every candidate goes through the very
+// same root computation (key_small, robust form), the smallest key wins, equal keys go to the lower list position.
+// The tree only skips spheres whose padded box the ray misses or enters beyond the best root so far.
+
+__device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 const& p, RayTerms const& r, uint32_t& best,
+                                                int& id)
+{
+    // slab test as (plane - o) * (1 / d): a zero component gives +-inf, 0 * inf = NaN is dropped by fminf / fmaxf
+    float const ix = fast_rcp(p.dx), iy = fast_rcp(p.dy), iz = fast_rcp(p.dz);
+    float tbest = best < kNoHitBits ? __uint_as_float(best) + r.eps : 3.0e38f;
+    int stack[kBvhStack];
+    int sp = 0;
+    int node = gl.bvh_root;
+    for(;;) {
+        if(node >= 0) {
+            float4 const n0 = gl.bvh_nodes[4 * node + 0];
+            float4 const n1 = gl.bvh_nodes[4 * node + 1];
+            float4 const n2 = gl.bvh_nodes[4 * node + 2];
+            float4 const n3 = gl.bvh_nodes[4 * node + 3];
+            float const ax0 = (n0.x - p.ox) * ix, ax1 = (n0.y - p.ox) * ix;
+            float const ay0 = (n0.z - p.oy) * iy, ay1 = (n0.w - p.oy) * iy;
+            float const az0 = (n2.x - p.oz) * iz, az1 = (n2.y - p.oz) * iz;
+            float const bx0 = (n1.x - p.ox) * ix, bx1 = (n1.y - p.ox) * ix;
+            float const by0 = (n1.z - p.oy) * iy, by1 = (n1.w - p.oy) * iy;
+            float const bz0 = (n2.z - p.oz) * iz, bz1 = (n2.w - p.oz) * iz;
+            float const amin = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+            float const amax = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tbest));
+            float const bmin = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
+            float const bmax = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), tbest));
+            bool const ha = amin <= amax, hb = bmin <= bmax;
+            int const ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
+            if(ha && hb) {
+                bool const a_first = amin <= bmin;
+                stack[sp++] = a_first ? cb : ca;
+                node = a_first ? ca : cb;
+                continue;
+            }
+            if(ha || hb) {
+                node = ha ? ca : cb;
+                continue;
+            }
+        }
+        else {
+            int const code = ~node;
+            int const first = code >> 3, count = (code & 7) + 1;
+            for(int k = 0; k < count; ++k) {
+                SmallGeo const s = gl.bvh_geo[first + k];
+                int const pw = gl.bvh_pos[first + k];
+                int const pos = pw & 0x7fffffff;
+                float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz;
+                float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));
+                float const sq = disc_sqrt(small_disc_far(cx, cy, cz, nb, s.r2, p));
+                float const h = nb - r.eps;
+                uint32_t const kn = __float_as_uint(h - sq);
+                uint32_t key = pw < 0 ? min(kn, __float_as_uint(h + sq)) : kn; // key_small<kBoth>
+                key = p.last == pos ? __float_as_uint(nb + h) : key;           // key_small<., kRobust>: standing on it
+                if(key < best || (key == best && pos < id)) {
+                    best = key;
+                    id = pos;
+                    tbest = key < kNoHitBits ? __uint_as_float(key) + r.eps : tbest;
+                }
+            }
+        }
+        if(sp == 0) {
+            break;
+        }
+        node = stack[--sp];
+    }
 }
 
 // Compile-time description of a scene's geometry lists; SN < 0 = run-time counts.
@@ -333,8 +420,11 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
         }
     }
     else {
-        int const nsn = cs.n_small_near, ns = cs.n_small;
+        int const nsn = gl.bvh_nodes != nullptr ? 0 : cs.n_small_near, ns = cs.n_small;
         int const nbn = cs.n_big_near, nb = cs.n_big;
+        if(gl.bvh_nodes != nullptr) {
+            bvh_closest_hit(gl, p, r, best, id);
+        }
 #pragma unroll 4
         for(int i = 0; i < nsn; ++i) {
             uint32_t const k = key_small<false, true>(gl.small_geo[i], p, r, p.last == i);
@@ -343,7 +433,7 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
                 id = i;
             }
         }
-        for(int i = nsn; i < ns; ++i) {
+        for(int i = gl.bvh_nodes != nullptr ? ns : nsn; i < ns; ++i) {
             uint32_t const k = key_small<true, true>(gl.small_geo[i], p, r, p.last == i);
             if(k < best) {
                 best = k;

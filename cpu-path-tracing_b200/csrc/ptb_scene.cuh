@@ -33,6 +33,7 @@ namespace ptb {
 
 constexpr int kMaxConstSpheres = 64; // geometry lists that live in __constant__ memory
 constexpr int kSmemShadeSpheres = 64; // shading planes staged in shared memory
+constexpr int kBvhStack = 64;         // traversal stack entries (ptb_path_f32.cuh); deeper trees fall back to the scan
 
 struct RawSphere // == pt::sphere, 88 bytes
 {
@@ -127,6 +128,11 @@ struct GeoLists
     SmallGeo const* small_geo;
     BigGeo const* big_geo;
     int const* order; // list position -> original sphere index
+    // Bounding-volume hierarchy over the small spheres (ptb_bvh.hpp), nullptr = scan the lists.
+    float4 const* bvh_nodes;   // 4 float4 per node
+    SmallGeo const* bvh_geo;   // spheres in leaf order
+    int const* bvh_pos;        // leaf slot -> list position, bit 31 set = both roots count (sphere.cpp:21-27)
+    int bvh_root;              // child code of the root
 };
 
 } // namespace ptb

@@ -70,7 +70,11 @@ enum
     PTB_INTEGRATOR_SMALLPT = 0x100, /* sandbox/main.cpp (stand-alone smallpt): tent-filter pinhole camera set with
                                        ptb_set_smallpt_camera, black miss, roulette after depth 5, IOR 1.5 glass
                                        that splits into reflection + refraction while depth <= 2, 2x2 sub-pixels */
-    PTB_INTEGRATOR_MASK = 0xF00
+    PTB_INTEGRATOR_MASK = 0xF00,
+    /* closest-hit query of scenes with more than 64 ordinary spheres (FP32 kernels) */
+    PTB_ACCEL_AUTO = 0x0000, /* bounding-volume hierarchy built at upload: same hits, O(log n) per ray */
+    PTB_ACCEL_SCAN = 0x1000, /* the reference's linear scan over every sphere (src/main.cpp:30-42) */
+    PTB_ACCEL_MASK = 0xF000
 };
 
 typedef struct ptb_stats

@@ -240,6 +240,62 @@ def test_wavefront_small_and_progressive(gpu):
     assert np.isclose(a[:, :3], b[:, :3], rtol=1e-4, atol=1e-4).all(axis=1).mean() > 0.97
 
 
+# ---- BASELINE config 5: 10 001 spheres, closest hit through the bounding-volume hierarchy ----------------------------------
+def test_spheres10k_fp64_against_oracle(gpu, oracle_port):
+    """Deterministic mode on the 10 001-sphere scene (linear scan in FP64, like the reference)."""
+    rng = np.random.default_rng(3)
+    W, H, n = 160, 90, 3000
+    sph, cfg = gpu.builtin_scene("spheres10k", W, H)
+    cam = gpu.camera_with_config(cfg)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, n)
+    ohit, orad, oray, _ = oracle_port.samples(sph, cam, W, H, 2, 41, xs, ys, sx, sy, ss)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        hit, rad, ray, _ = r.trace_samples(41, xs, ys, sx, sy, ss, gpu.PRECISION_FP64)
+    assert np.array_equal(hit, ohit)
+    assert np.array_equal(ray, oray)
+    assert (rel_err(rad, orad) <= REL_TOL).mean() >= 0.999
+
+
+def test_spheres10k_hierarchy_gives_the_scan_s_hits(gpu, oracle_port):
+    """PTB_ACCEL_AUTO (hierarchy) against PTB_ACCEL_SCAN (every sphere, main.cpp:30-42) in FP32: the same sphere test
+    decides every hit, so per-sample primary hits and radiance are IDENTICAL; and both agree with the FP64 oracle."""
+    rng = np.random.default_rng(5)
+    W, H, n = 160, 90, 20000
+    sph, cfg = gpu.builtin_scene("spheres10k", W, H)
+    cam = gpu.camera_with_config(cfg)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, n)
+    ohit, orad, _, _ = oracle_port.samples(sph, cam, W, H, 2, 43, xs[:4000], ys[:4000], sx[:4000], sy[:4000], ss[:4000])
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        hit_a, rad_a, ray_a, _ = r.trace_samples(43, xs, ys, sx, sy, ss, gpu.PRECISION_FP32 | gpu.ACCEL_AUTO)
+        hit_s, rad_s, ray_s, _ = r.trace_samples(43, xs, ys, sx, sy, ss, gpu.PRECISION_FP32 | gpu.ACCEL_SCAN)
+    assert np.array_equal(hit_a, hit_s)
+    assert np.array_equal(rad_a, rad_s), "the hierarchy must not change a single bounce"
+    assert np.isfinite(rad_a).all()
+    assert (hit_a[:4000] == ohit).mean() >= 0.999
+    rel = rel_err(rad_a[:4000], orad)
+    assert (rel <= 1e-3).mean() >= 0.97
+    se = np.sqrt((rad_a[:4000].var(axis=0) + orad.var(axis=0)) / 4000)
+    assert np.abs((rad_a[:4000].mean(axis=0) - orad.mean(axis=0)) / se).max() < 4.0
+
+
+@pytest.mark.parametrize("variant", ["VARIANT_MEGAKERNEL", "VARIANT_MEGAKERNEL_SORTED"])
+def test_spheres10k_render_hierarchy_against_scan(gpu, variant):
+    W, H, S = 96, 54, 4
+    sph, cfg = gpu.builtin_scene("spheres10k", W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(9, 0, S, gpu.PRECISION_FP32 | getattr(gpu, variant) | gpu.ACCEL_AUTO)
+        a, st_a = r.download_accum(), r.stats()
+        r.clear()
+        r.render(9, 0, S, gpu.PRECISION_FP32 | getattr(gpu, variant) | gpu.ACCEL_SCAN)
+        b, st_b = r.download_accum(), r.stats()
+    assert np.all(a[:, 3] == S) and np.all(b[:, 3] == S) and np.isfinite(a).all()
+    assert (st_a.rays, st_a.hits_diffuse, st_a.hits_specular, st_a.hits_dielectric) == \
+        (st_b.rays, st_b.hits_diffuse, st_b.hits_specular, st_b.hits_dielectric)
+    assert np.isclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-5).all()  # same paths; only the order of the additions differs
+    assert st_a.last_render_ms < st_b.last_render_ms  # and that is the point of it
+
+
 # ---- semantics that must survive the boundary (SURVEY.md section 8b) ------------------------------------------------------
 def test_progressive_accumulation_and_sample_split(gpu):
     """render(0,8) == render(0,3) + render(3,5): what lets ranks split the samples of a sub-pixel."""
@@ -398,7 +454,7 @@ def test_error_behaviour(gpu):
             r.set_image(0, 8, 2)
         r.set_image(8, 8, 2)
         with pytest.raises(gpu.PtbError) as e:
-            r.render(1, 0, 1, 0x1000)  # unknown flag
+            r.render(1, 0, 1, 0x10000)  # unknown flag
         assert e.value.code == -1
         with pytest.raises(gpu.PtbError):
             r.render(1, 0xFFFFFFFF, 2)  # sample range overflow
