@@ -265,6 +265,30 @@ PackedScene pack_geometry(ptb_context* ctx)
             lists[(big ? 2 : 0) + (near_only ? 0 : 1)].push_back(i);
         }
     }
+    // Mirror-image pairs: an axis group of exactly two spheres with opposite centres and one radius (checked on the
+    // FP32 coefficients the kernel will read); the +C sphere goes first (ptb_path_f32.cuh: key_big_pair).
+    int pair_mask = 0;
+    for(int a = 0; a < 3; ++a) {
+        std::vector<int>& l = big_near[a];
+        if(l.size() != 2) {
+            continue;
+        }
+        auto const coef = [&](int i, float& g, float& K) {
+            double const R = s[i].radius, k = 1.0 / (2.0 * R);
+            double const c[3] = { s[i].px - sh[0], s[i].py - sh[1], s[i].pz - sh[2] };
+            g = static_cast<float>(-k * c[a]);
+            K = static_cast<float>(k * ((c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) - R * R));
+        };
+        float g0, K0, g1, K1;
+        coef(l[0], g0, K0);
+        coef(l[1], g1, K1);
+        if(s[l[0]].radius == s[l[1]].radius && g0 == -g1 && g0 != 0.0f && K0 == K1) {
+            if(g0 > 0.0f) { // g = -k c: the +C sphere has the negative g
+                std::swap(l[0], l[1]);
+            }
+            pair_mask |= 1 << a;
+        }
+    }
     for(auto const& l : big_near) {
         lists[2].insert(lists[2].end(), l.begin(), l.end());
     }
@@ -276,6 +300,7 @@ PackedScene pack_geometry(ptb_context* ctx)
     out.counts.big_y = static_cast<int>(big_near[1].size());
     out.counts.big_z = static_cast<int>(big_near[2].size());
     out.counts.uniform_k = any_big && uniform_k;
+    out.counts.pair_mask = out.counts.uniform_k ? pair_mask : 0;
     // index-in-key truncates t by < 2^-19 relative: allowed while 2e-6 * (scene extent) << epsilon = 1e-4.
     // Extent = reach of the ordinary spheres and the cameras from the frame origin.
     double extent = 0.0;
@@ -296,6 +321,9 @@ PackedScene pack_geometry(ptb_context* ctx)
         extent = std::max(extent, reach(ctx->sb_cam8));
     }
     out.counts.embed_ok = extent <= 8.0;
+    if(!out.counts.embed_ok) {
+        out.counts.pair_mask = 0; // the paired test exists for the index-in-key kernels only
+    }
     out.counts.fits_const = out.counts.small_near + out.counts.small_both <= kMaxConstSpheres &&
                             out.counts.big_near + out.counts.big_both <= kMaxConstSpheres;
     for(auto const& l : lists) {

@@ -269,24 +269,26 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
 // (small near-only, small both-roots, big near-only, big both-roots) list lengths with a fully
 // unrolled kernel.  Everything else runs the generic run-time-count variant.
 #define PTB_MEGA_SPECIALISATIONS(X) \
-    X(2, 1, 5, 0, 2, 2, 1, true, true)   /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball | glass ball | 5 R=1e6 walls on the frame axes */ \
-    X(3, 1, 1, 0, 0, 1, 0, true, true)   /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100, on the y axis)                       */ \
-    X(2, 2, 1, 0, 0, 1, 0, true, true)   /* depth-of-field scene (BASELINE config 4): two glass spheres                                             */ \
-    X(2, 1, 5, 0, 0, 0, 0, false, true)  /* box scenes in a frame where the walls are not axis spheres                                             */ \
-    X(0, 3, 0, 5, 0, 0, 0, false, true)  /* box scenes with the camera inside every sphere's reach: all both-roots                                 */ \
-    X(3, 1, 0, 6, 0, 0, 0, true, false)  /* sandbox/main.cpp: 2 mirrors + light | glass | six R=1e5 walls seen from INSIDE; ~300 units across     */ \
-    X(1, 0, 0, 0, 0, 0, 0, false, true) \
-    X(0, 1, 0, 0, 0, 0, 0, false, true) \
-    X(8, 0, 0, 0, 0, 0, 0, false, true)
+    X(2, 1, 5, 0, 2, 2, 1, true, true, 3)   /* box_scene.hpp / box_mirror_scene.hpp: light + mirror ball | glass ball | 5 R=1e6 walls on the frame axes, left/right and top/bottom as mirror-image pairs */ \
+    X(2, 1, 5, 0, 2, 2, 1, true, true, 0)   /* the same without the pairing                                                                          */ \
+    X(3, 1, 1, 0, 0, 1, 0, true, true, 0)   /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100, on the y axis)                       */ \
+    X(2, 2, 1, 0, 0, 1, 0, true, true, 0)   /* depth-of-field scene (BASELINE config 4): two glass spheres                                             */ \
+    X(2, 1, 5, 0, 0, 0, 0, false, true, 0)  /* box scenes in a frame where the walls are not axis spheres                                             */ \
+    X(0, 3, 0, 5, 0, 0, 0, false, true, 0)  /* box scenes with the camera inside every sphere's reach: all both-roots                                 */ \
+    X(3, 1, 0, 6, 0, 0, 0, true, false, 0)  /* sandbox/main.cpp: 2 mirrors + light | glass | six R=1e5 walls seen from INSIDE; ~300 units across     */ \
+    X(1, 0, 0, 0, 0, 0, 0, false, true, 0) \
+    X(0, 1, 0, 0, 0, 0, 0, false, true, 0) \
+    X(8, 0, 0, 0, 0, 0, 0, false, true, 0)
 
-#define PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) \
+#define PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em, pm) \
     ((c).small_near == (a) && (c).small_both == (b) && (c).big_near == (cc) && (c).big_both == (d) && (c).big_x == (bx) && \
-     (c).big_y == (by) && (c).big_z == (bz) && (c).uniform_k == (uk) && (c).embed_ok == (em) && (c).fits_const)
+     (c).big_y == (by) && (c).big_z == (bz) && (c).uniform_k == (uk) && (c).embed_ok == (em) && (c).pair_mask == (pm) && \
+     (c).fits_const)
 
 bool megakernel_has_specialisation(SceneCounts const& c)
 {
-#define X(a, b, cc, d, bx, by, bz, uk, em) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em)) { \
+#define X(a, b, cc, d, bx, by, bz, uk, em, pm) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em, pm)) { \
         return true; \
     }
     PTB_MEGA_SPECIALISATIONS(X)
@@ -326,9 +328,9 @@ template<class Integ>
 static cudaError_t launch_mega_integrator(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream)
 {
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d, bx, by, bz, uk, em) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) && smem) { \
-        return launch_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, true, Integ>(p, sm_count, stream); \
+#define X(a, b, cc, d, bx, by, bz, uk, em, pm) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em, pm) && smem) { \
+        return launch_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em), (pm)>, true, Integ>(p, sm_count, stream); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X
@@ -444,9 +446,9 @@ static cudaError_t launch_probe_integrator(ProbeParams const& p, SceneCounts con
 {
     unsigned const threads = kMegaThreads;
     unsigned const blocks = (p.count + threads - 1) / threads;
-#define X(a, b, cc, d, bx, by, bz, uk, em) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em)) { \
-        probe_f32_kernel<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, Integ><<<blocks, threads, 0, stream>>>(p, shade, geo); \
+#define X(a, b, cc, d, bx, by, bz, uk, em, pm) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em, pm)) { \
+        probe_f32_kernel<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em), (pm)>, Integ><<<blocks, threads, 0, stream>>>(p, shade, geo); \
         return cudaGetLastError(); \
     }
     PTB_MEGA_SPECIALISATIONS(X)

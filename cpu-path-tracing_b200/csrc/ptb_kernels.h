@@ -52,6 +52,7 @@ struct SceneCounts
     int big_x = 0, big_y = 0, big_z = 0; // prefix of the near-only big list: centres on a frame axis
     bool uniform_k = false;              // every big sphere has the same radius
     bool embed_ok = true;                // scene small enough against epsilon for index-in-key (ptb_path_f32.cuh)
+    int pair_mask = 0;                   // bit a: the two spheres of axis group a are mirror images (+side listed first)
 };
 // True when a fully unrolled kernel exists for these list lengths.
 bool megakernel_has_specialisation(SceneCounts const& c);

@@ -401,9 +401,9 @@ template<int kInline>
 static cudaError_t launch_sorted_inline(RenderParamsF32 const& p, SceneCounts const& c, int sm_count, cudaStream_t stream)
 {
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d, bx, by, bz, uk, em) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) && smem) { \
-        return launch_sorted_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, true, kInline>(p, sm_count, stream); \
+#define X(a, b, cc, d, bx, by, bz, uk, em, pm) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em, pm) && smem) { \
+        return launch_sorted_one<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em), (pm)>, true, kInline>(p, sm_count, stream); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X

@@ -265,6 +265,30 @@ __device__ __forceinline__ uint32_t key_big_axis(BigGeo const& b, PathF32 const&
     return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
 }
 
+// Two near-only axis spheres that are mirror images of each other (the left / right and top / bottom walls of
+// the box scenes: centres +-C on a frame axis, one radius).  A ray outside a sphere and moving AWAY from its
+// centre never meets it, and with |C| ~ 1e6 "towards the +C centre" is the sign of the direction's axis component
+// for every ray that could reach the wall before t ~ 1e5.  So the pair costs one test: with s = sign(d_a),
+// half_b = k o.d - |d_a| G and c' = k o.o + K - s (2 o_a) G, G = k C, are the selected sphere's coefficients exactly
+// (same bits as key_big_axis gives for it).  `b` is the +C sphere; returns its key with `sel` = 0 for the +C
+// sphere, 1 for the -C one.
+template<int AXIS>
+__device__ __forceinline__ uint32_t key_big_pair(BigGeo const& b, PathF32 const& p, RayTerms const& r, uint32_t& sel)
+{
+    float const da = AXIS == 0 ? p.dx : (AXIS == 1 ? p.dy : p.dz);
+    float const oa2 = AXIS == 0 ? r.o2x : (AXIS == 1 ? r.o2y : r.o2z);
+    float const G = fabsf(AXIS == 0 ? b.gx : (AXIS == 1 ? b.gy : b.gz));
+    uint32_t const sign = __float_as_uint(da) & 0x80000000u;
+    float const hb = fmaf(-fabsf(da), G, r.kod);
+    float const cp = fmaf(-__uint_as_float(__float_as_uint(oa2) ^ sign), G, r.koo + b.K);
+    float const disc = fmaf(hb, hb, -(b.k * cp));
+    float const m = disc_sqrt(disc) + fabsf(hb);
+    uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
+    float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
+    sel = sign >> 31;
+    return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
+}
+
 // ---- closest hit through the bounding-volume hierarchy (ptb_bvh.hpp) -------------
 // Same answer as the linear scan of main.cpp:30-42 over the small spheres: every candidate goes through the very
 // same root computation (key_small, robust form), the smallest key wins, equal keys go to the lower list position.
@@ -344,9 +368,16 @@ __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 cons
 //   hit point by up to 2e-6 * t, which must stay far below epsilon = 1e-4 (a refracted ray
 //   leaving a glass sphere re-hits it from inside otherwise -- seen on the sandbox scene, whose
 //   extent is ~300 units).
-template<int SN, int SB, int BN, int BB, int BX = 0, int BY = 0, int BZ = 0, bool UK = false, bool EM = true>
+//   PM = bit a set: axis group a is ONE mirror-image pair (centres +C and -C on the axis, same radius, the +C
+//   sphere listed first): a ray moving towards +a can only meet the +C sphere and vice versa, so one test with
+//   the signs folded in serves both (key_big_pair).
+template<int SN, int SB, int BN, int BB, int BX = 0, int BY = 0, int BZ = 0, bool UK = false, bool EM = true, int PM = 0>
 struct SceneShape
 {
+    static constexpr int pair_mask = PM;
+    static_assert(SN < 0 || (((PM & 1) == 0 || BX == 2) && ((PM & 2) == 0 || BY == 2) && ((PM & 4) == 0 || BZ == 2)),
+                  "a paired axis group holds exactly two spheres");
+    static_assert(PM == 0 || (UK && EM), "pairs need the shared radius and index-in-key");
     static constexpr bool embed = EM;
     static constexpr int small_near = SN, small_both = SB, big_near = BN, big_both = BB;
     static constexpr int big_x = BX, big_y = BY, big_z = BZ;
@@ -397,6 +428,20 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
 #pragma unroll
         for(int i = 0; i < NB; ++i) {
             uint32_t k;
+            constexpr int x0 = 0, y0 = Shape::big_x, z0 = Shape::big_x + Shape::big_y;
+            if(((Shape::pair_mask & 1) != 0 && i == x0) || ((Shape::pair_mask & 2) != 0 && i == y0) ||
+               ((Shape::pair_mask & 4) != 0 && i == z0)) {
+                uint32_t sel;
+                k = i == x0 && (Shape::pair_mask & 1) != 0   ? key_big_pair<0>(cs.big_geo[i], p, r, sel)
+                    : i == y0 && (Shape::pair_mask & 2) != 0 ? key_big_pair<1>(cs.big_geo[i], p, r, sel)
+                                                             : key_big_pair<2>(cs.big_geo[i], p, r, sel);
+                best = min(best, (k & (kKeepReg ? keep_reg : keep)) | (static_cast<uint32_t>(NS + i) + sel));
+                continue;
+            }
+            if(((Shape::pair_mask & 1) != 0 && i == x0 + 1) || ((Shape::pair_mask & 2) != 0 && i == y0 + 1) ||
+               ((Shape::pair_mask & 4) != 0 && i == z0 + 1)) {
+                continue; // the -C sphere of a pair: answered together with its partner
+            }
             if(i < Shape::big_x) {
                 k = key_big_axis<0, Shape::uniform_k>(cs.big_geo[i], p, r);
             }

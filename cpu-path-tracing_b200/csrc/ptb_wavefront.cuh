@@ -414,9 +414,9 @@ cudaError_t launch_wavefront(WavefrontBuffers const& buf, RenderParamsF32 const&
     w.ctr = buf.counters;
     w.pool = buf.pool;
     bool const smem = p.n_total <= kSmemShadeSpheres;
-#define X(a, b, cc, d, bx, by, bz, uk, em) \
-    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em) && smem) { \
-        return wf_run<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em)>, true>(w, p, sm_count, stream, launches); \
+#define X(a, b, cc, d, bx, by, bz, uk, em, pm) \
+    if(PTB_COUNTS_MATCH(c, a, b, cc, d, bx, by, bz, uk, em, pm) && smem) { \
+        return wf_run<SceneShape<(a), (b), (cc), (d), (bx), (by), (bz), (uk), (em), (pm)>, true>(w, p, sm_count, stream, launches); \
     }
     PTB_MEGA_SPECIALISATIONS(X)
 #undef X
