@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
         __syncthreads();
     }
     // shading plane k of sphere i: shared window byte address shade_base + (k * stride + i) * 16, or the global array
-    uint32_t const shade_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_shade));
+    // (through a shuffle: a value the compiler can re-derive from special registers gets re-derived in the loop --
+    //  S2R + LEA at the head of the shading chain -- instead of living in a register)
+    uint32_t const shade_base = __shfl_sync(0xffffffffu, static_cast<uint32_t>(__cvta_generic_to_shared(s_shade)), 0);
     constexpr uint32_t kShadePlane = kSmemShadeSpheres * 16u;
     float4 const* const gshade = prm.shade.a; // the global planes are contiguous (ptb_api.cpp: shade_planes)
     int const gstride = prm.n_total;
