@@ -192,11 +192,30 @@ def run_reference(args, scene, width, height, spp):
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout
+    when NCCL_DEBUG asks for it): keep the real stdout for the result line and point fd 1 at stderr for everybody else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -380,7 +399,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind,
                                     "sample": f"{scene} {bw}x{bh} at {4 * bs} spp ({bw * bh * 4 * bs / 1e6:.1f} Mpaths, {dt:.1f} s), "
                                               f"all {cores} host threads, OpenMP dynamic rows"}
-        print(json.dumps(line))
+        _emit(line)
     dr.close()
     if world > 1:
         dist.destroy_process_group()
