@@ -733,8 +733,9 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
-    if(spheres == nullptr || count == 0 || stride < PTB_SPHERE_BYTES || count > (1u << 24)) {
-        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need count >= 1 spheres of stride >= 88 bytes");
+    // count == 0 is a scene: every ray misses and sees the sky (main.cpp:114-120), spheres may then be null
+    if((spheres == nullptr && count != 0) || stride < PTB_SPHERE_BYTES || count > (1u << 24)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need spheres of stride >= 88 bytes (at most 2^24)");
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->h_spheres.resize(count);
@@ -757,8 +758,10 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
         PTB_CUDA(ctx, cudaMalloc(&ctx->d_spheres, count * sizeof(RawSphere)));
         ctx->d_spheres_cap = count;
     }
-    PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_spheres, ctx->h_spheres.data(), count * sizeof(RawSphere),
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    if(count > 0) {
+        PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_spheres, ctx->h_spheres.data(), count * sizeof(RawSphere),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->have_scene = true;
     {
         // first guess for the sorted megakernel: surface seen by a ray ~ radius^2, walls (huge spheres) capped

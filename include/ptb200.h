@@ -110,7 +110,10 @@ int ptb_synchronize(ptb_context* ctx);
 
 /* ---- inputs ------------------------------------------------------------------ */
 /* The sphere list of pt::scene (src/scene.hpp:12-16), in index order (the
- * closest-hit tie rule of src/main.cpp:35 depends on it).  `stride` >= 88. */
+ * closest-hit tie rule of src/main.cpp:35 depends on it).  `stride` >= 88.
+ * count == 0 is valid (an empty pt::scene: every ray sees the sky, main.cpp:114-120).
+ * More than 64 ordinary-sized spheres: a bounding-volume hierarchy is built here
+ * (host side, milliseconds) for the FP32 kernels -- see PTB_ACCEL_*. */
 int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t stride);
 /* A derived pt::camera, i.e. the result of pt::camera::with_config (src/main.cpp:209). */
 int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes);

@@ -296,6 +296,47 @@ def test_spheres10k_render_hierarchy_against_scan(gpu, variant):
     assert st_a.last_render_ms < st_b.last_render_ms  # and that is the point of it
 
 
+# ---- degenerate scenes ----------------------------------------------------------------------------------------------------
+def test_empty_scene_is_all_sky(gpu, oracle_port):
+    """No spheres: every ray misses (main.cpp:114-120).  FP64 equals the oracle to rounding, every FP32 variant agrees."""
+    W, H, S = 48, 27, 3
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    sph = gpu.builtin_scene("simple", W, H)[0][:0].copy()
+    ref = oracle_port.render(sph, cam, W, H, S, 2, 4, 0)
+    assert ref.min() > 0.4  # the sky gradient (0.5..1 per channel), nothing else
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(4, 0, S, gpu.PRECISION_FP64)
+        assert np.abs(r.resolve() - ref).max() < 1e-12  # the order of the S additions into a slot is not fixed
+        for v in (gpu.VARIANT_MEGAKERNEL, gpu.VARIANT_MEGAKERNEL_SORTED, gpu.VARIANT_WAVEFRONT):
+            r.clear()
+            r.render(4, 0, S, gpu.PRECISION_FP32 | v)
+            st = r.stats()
+            assert st.rays == st.paths == W * H * 4 * S and st.hits_diffuse == 0
+            assert np.abs(r.resolve() - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("refl", [0, 1, 2])
+def test_single_sphere_of_each_material(gpu, oracle_port, refl):
+    """One sphere in front of the camera, each material in turn (exercises the one-sphere kernel shapes; the glass
+    ball is the both-roots-only list)."""
+    W, H, S = 64, 36, 6
+    sph, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    one = sph[1:2].copy()
+    one["reflection"][0] = refl
+    ref = oracle_port.render(one, cam, W, H, S, 2, 6, 0)
+    with make_renderer(gpu, one, cam, W, H) as r:
+        r.render(6, 0, S, gpu.PRECISION_FP64)
+        assert (np.abs(r.resolve() - ref) <= 1e-9).mean() >= 0.998
+        for v in (gpu.VARIANT_MEGAKERNEL, gpu.VARIANT_MEGAKERNEL_SORTED):
+            r.clear()
+            r.render(6, 0, S, gpu.PRECISION_FP32 | v)
+            acc = r.download_accum()
+            assert np.all(acc[:, 3] == S) and np.isfinite(acc).all()
+            assert np.abs(r.resolve() - ref).mean() < 2e-3
+
+
 # ---- semantics that must survive the boundary (SURVEY.md section 8b) ------------------------------------------------------
 def test_progressive_accumulation_and_sample_split(gpu):
     """render(0,8) == render(0,3) + render(3,5): what lets ranks split the samples of a sub-pixel."""
