@@ -1,0 +1,54 @@
+"""Apply the INTEGRATION.md section 1 patch to the reference's src/main.cpp, writing the result somewhere ELSE
+(a build directory; the reference tree is read-only and its sources are never copied into this repository):
+
+    python oracle/ref/make_dropin.py /root/reference/src/main.cpp /tmp/build/main_dropin.cpp
+
+Everything that builds the scene, the camera and the PPM file is kept; the taskflow row-task block
+(src/main.cpp:214-236) becomes seven calls into include/ptb200.h.  oracle/Makefile compiles the result with the
+reference's own headers and translation units into oracle/_ref/cpu_path_tracer_b200 -- the reference PROGRAM running
+on the B200 library -- which tests/test_reference_dropin.py links-checks on CPU and runs on the GPU box.
+"""
+import re
+import sys
+
+ABI_BLOCK = '''    static_assert(sizeof(pt::sphere) == PTB_SPHERE_BYTES && sizeof(pt::camera) == PTB_CAMERA_BYTES,
+                  "the reference's own records cross the boundary as they are");
+    ptb_context* gpu = nullptr;
+    if(ptb_create(/*device*/ 0, &gpu) != PTB_OK) {
+        std::cerr << ptb_last_error(nullptr) << '\\n';
+        return 1;
+    }
+    int rc = ptb_upload_scene(gpu, some_scene.spheres.data(), some_scene.spheres.size(), sizeof(pt::sphere));
+    rc = rc == PTB_OK ? ptb_set_camera(gpu, &cam, sizeof(cam)) : rc;
+    rc = rc == PTB_OK ? ptb_set_image(gpu, width, height, num_subpixels) : rc;
+    rc = rc == PTB_OK ? ptb_render(gpu, /*seed*/ 1, /*first_sample*/ 0, static_cast<unsigned>(samps),
+                                   PTB_VARIANT_MEGAKERNEL_SORTED | PTB_PRECISION_FP32)
+                      : rc;
+    rc = rc == PTB_OK ? ptb_resolve(gpu, reinterpret_cast<double*>(image.data())) : rc;
+    if(rc != PTB_OK) {
+        std::cerr << ptb_last_error(gpu) << '\\n';
+        return 1;
+    }
+    ptb_destroy(gpu);
+'''
+
+
+def patch(text: str) -> str:
+    if "#include <taskflow/taskflow.hpp>" not in text:
+        raise SystemExit("make_dropin: taskflow include not found -- has the reference changed?")
+    text = text.replace("#include <taskflow/taskflow.hpp>", "#include <ptb200.h> // C ABI of the B200 render loop")
+    block = re.compile(r"^    tf::Executor executor\{\};\n.*?^    executor\.run\(taskflow\)\.wait\(\);\n", re.S | re.M)
+    text, n = block.subn(lambda _m: ABI_BLOCK, text)
+    if n != 1:
+        raise SystemExit("make_dropin: the row-task block (src/main.cpp:214-236) was not found exactly once")
+    if "tf::" in text:
+        raise SystemExit("make_dropin: taskflow is still referenced after the patch")
+    return text
+
+
+if __name__ == "__main__":
+    src, dst = sys.argv[1], sys.argv[2]
+    with open(src) as f:
+        out = patch(f.read())
+    with open(dst, "w") as f:
+        f.write(out)
