@@ -102,8 +102,14 @@ def test_nsub_other_than_two(gpu, oracle_port):
             r.clear()
             r.render(8, 0, S, gpu.PRECISION_FP32)
             img32 = r.resolve()
+            r.clear()
+            r.render(8, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
+            img32s = r.resolve()
+            acc = r.download_accum()
         assert (np.abs(img64 - ref) <= 1e-9).mean() >= 0.995
         assert np.abs(img32 - ref).mean() < 5e-3
+        assert np.all(acc[:, 3] == S) and acc.shape[0] == W * H * nsub * nsub
+        assert np.abs(img32s - img32).max() < 1e-5  # the two megakernels trace the same paths
 
 
 # ---- (b) throughput mode -----------------------------------------------------------------------------------------
