@@ -39,7 +39,11 @@
 namespace ptb {
 
 constexpr int kSortedThreads = 128;
+#ifdef PTB_SORTED_BLOCKS
+constexpr int kSortedBlocksPerSm = PTB_SORTED_BLOCKS; // dev/build_variant.sh experiments
+#else
 constexpr int kSortedBlocksPerSm = 6;
+#endif
 constexpr int kSortedRing = 64;     // entries per ring, power of two
 constexpr int kEmissiveBit = 0x100; // in ShadePlanes::b.w next to the reflection tag (ptb_api.cpp: pack_geometry)
 
