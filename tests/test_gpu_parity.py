@@ -302,6 +302,45 @@ def test_spheres10k_render_hierarchy_against_scan(gpu, variant):
     assert st_a.last_render_ms < st_b.last_render_ms  # and that is the point of it
 
 
+# ---- BASELINE config 3 at its full image size: properties that do not depend on the size ------------------------------------
+def test_full_size_box_mirror_properties(gpu, oracle_port):
+    """1920x1080 box_mirror (the north-star workload) at 64 spp, through the product path.  Checked: every one of the
+    8.3 M sub-pixel slots received exactly its samples; the path statistics are the reference's (SURVEY.md 8c:
+    12.33 rays, 0.53 diffuse / 9.81 mirror / 0.99 glass hits per path); rendering the samples in two passes gives the
+    image of one pass (what progressive rendering and the multi-GPU sample split rely on); and the 8x8 box-filtered
+    image is the oracle's 240x135 image of the same scene within Monte-Carlo noise."""
+    W, H, S = 1920, 1080, 16
+    sph, cfg = gpu.builtin_scene("box_mirror", W, H)
+    cam = gpu.camera_with_config(cfg)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(77, 0, S, flags)
+        one = r.download_accum()
+        st = r.stats()
+        img = r.resolve()
+        r.clear()
+        r.render(77, 0, 5, flags)
+        r.render(77, 5, S - 5, flags)
+        two = r.download_accum()
+    assert one.shape == (W * H * 4, 4) and np.all(one[:, 3] == S) and np.all(two[:, 3] == S)
+    assert np.isfinite(one).all()
+    paths = W * H * 4 * S
+    assert st.paths == paths
+    assert abs(st.rays / paths - 12.33) < 0.15
+    assert abs(st.hits_diffuse / paths - 0.53) < 0.03
+    assert abs(st.hits_specular / paths - 9.81) < 0.15
+    assert abs(st.hits_dielectric / paths - 0.99) < 0.05
+    assert np.isclose(one[:, :3], two[:, :3], rtol=1e-5, atol=1e-5).all()
+    # size-independent image check: an oracle pixel at 240x135 covers 8x8 pixels of this render
+    sph_s, cfg_s = gpu.builtin_scene("box_mirror", W // 8, H // 8)
+    ref = oracle_port.render(sph_s, gpu.camera_with_config(cfg_s), W // 8, H // 8, 16, 2, 5, 0)
+    small = img.reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3))
+    dark = ref.max(axis=2) < 0.8  # the per-sub-pixel clamp (main.cpp:195) is not linear: compare below it
+    assert dark.mean() > 0.5
+    assert np.abs(small - ref)[dark].mean() < 0.02
+    assert abs(small[dark].mean() - ref[dark].mean()) < 0.005
+
+
 # ---- degenerate scenes ----------------------------------------------------------------------------------------------------
 def test_empty_scene_is_all_sky(gpu, oracle_port):
     """No spheres: every ray misses (main.cpp:114-120).  FP64 equals the oracle to rounding, every FP32 variant agrees."""
