@@ -471,8 +471,14 @@ int rebuild_device_scene(ptb_context* ctx)
         for(int i = 0; i < n_small; ++i) {
             ctx->cs.small_geo[i] = ps.small_geo[static_cast<size_t>(i)];
         }
+        int const n_axis = ps.counts.big_x + ps.counts.big_y + ps.counts.big_z;
         for(int i = 0; i < n_big; ++i) {
-            ctx->cs.big_geo[i] = ps.big_geo[static_cast<size_t>(i)];
+            BigGeo const& b = ps.big_geo[static_cast<size_t>(i)];
+            ctx->cs.big_geo[i] = b;
+            // axis spheres: the one non-zero component of g (x group first, then y, then z) and K
+            int const axis = i < ps.counts.big_x ? 0 : (i < ps.counts.big_x + ps.counts.big_y ? 1 : 2);
+            ctx->cs.axis_coef[2 * i] = i < n_axis ? (axis == 0 ? b.gx : (axis == 1 ? b.gy : b.gz)) : 0.0f;
+            ctx->cs.axis_coef[2 * i + 1] = b.K;
         }
         for(int i = 0; i < n; ++i) {
             ctx->cs.order[i] = ps.order[static_cast<size_t>(i)];

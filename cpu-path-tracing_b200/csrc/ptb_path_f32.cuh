@@ -251,14 +251,13 @@ __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, R
 // 3-term dot products shrink to one FFMA each.  kUniformK: all big spheres share k = 1/2R, so
 // k*od and k*oo are per-ray values.  Exact -- nothing is approximated.
 template<int AXIS, bool kUniformK>
-__device__ __forceinline__ uint32_t key_big_axis(BigGeo const& b, PathF32 const& p, RayTerms const& r)
+__device__ __forceinline__ uint32_t key_big_axis(float ga, float K, float k, PathF32 const& p, RayTerms const& r)
 {
     float const da = AXIS == 0 ? p.dx : (AXIS == 1 ? p.dy : p.dz);
     float const oa2 = AXIS == 0 ? r.o2x : (AXIS == 1 ? r.o2y : r.o2z);
-    float const ga = AXIS == 0 ? b.gx : (AXIS == 1 ? b.gy : b.gz);
-    float const hb = fmaf(da, ga, kUniformK ? r.kod : b.k * r.od);
-    float const cp = fmaf(oa2, ga, kUniformK ? r.koo + b.K : fmaf(b.k, r.oo, b.K));
-    float const disc = fmaf(hb, hb, -(b.k * cp));
+    float const hb = fmaf(da, ga, kUniformK ? r.kod : k * r.od);
+    float const cp = fmaf(oa2, ga, kUniformK ? r.koo + K : fmaf(k, r.oo, K));
+    float const disc = fmaf(hb, hb, -(k * cp));
     float const m = disc_sqrt(disc) + fabsf(hb);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
@@ -270,18 +269,18 @@ __device__ __forceinline__ uint32_t key_big_axis(BigGeo const& b, PathF32 const&
 // centre never meets it, and with |C| ~ 1e6 "towards the +C centre" is the sign of the direction's axis component
 // for every ray that could reach the wall before t ~ 1e5.  So the pair costs one test: with s = sign(d_a),
 // half_b = k o.d - |d_a| G and c' = k o.o + K - s (2 o_a) G, G = k C, are the selected sphere's coefficients exactly
-// (same bits as key_big_axis gives for it).  `b` is the +C sphere; returns its key with `sel` = 0 for the +C
+// (same bits as key_big_axis gives for it).  (ga, K) are the +C sphere's; returns its key with `sel` = 0 for the +C
 // sphere, 1 for the -C one.
 template<int AXIS>
-__device__ __forceinline__ uint32_t key_big_pair(BigGeo const& b, PathF32 const& p, RayTerms const& r, uint32_t& sel)
+__device__ __forceinline__ uint32_t key_big_pair(float ga, float K, float k, PathF32 const& p, RayTerms const& r, uint32_t& sel)
 {
     float const da = AXIS == 0 ? p.dx : (AXIS == 1 ? p.dy : p.dz);
     float const oa2 = AXIS == 0 ? r.o2x : (AXIS == 1 ? r.o2y : r.o2z);
-    float const G = fabsf(AXIS == 0 ? b.gx : (AXIS == 1 ? b.gy : b.gz));
+    float const G = fabsf(ga);
     uint32_t const sign = __float_as_uint(da) & 0x80000000u;
     float const hb = fmaf(-fabsf(da), G, r.kod);
-    float const cp = fmaf(-__uint_as_float(__float_as_uint(oa2) ^ sign), G, r.koo + b.K);
-    float const disc = fmaf(hb, hb, -(b.k * cp));
+    float const cp = fmaf(-__uint_as_float(__float_as_uint(oa2) ^ sign), G, r.koo + K);
+    float const disc = fmaf(hb, hb, -(k * cp));
     float const m = disc_sqrt(disc) + fabsf(hb);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
@@ -432,9 +431,10 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
             if(((Shape::pair_mask & 1) != 0 && i == x0) || ((Shape::pair_mask & 2) != 0 && i == y0) ||
                ((Shape::pair_mask & 4) != 0 && i == z0)) {
                 uint32_t sel;
-                k = i == x0 && (Shape::pair_mask & 1) != 0   ? key_big_pair<0>(cs.big_geo[i], p, r, sel)
-                    : i == y0 && (Shape::pair_mask & 2) != 0 ? key_big_pair<1>(cs.big_geo[i], p, r, sel)
-                                                             : key_big_pair<2>(cs.big_geo[i], p, r, sel);
+                float const ga = cs.axis_coef[2 * i], K = cs.axis_coef[2 * i + 1], kk = cs.big_geo[0].k; // pairs: one radius
+                k = i == x0 && (Shape::pair_mask & 1) != 0   ? key_big_pair<0>(ga, K, kk, p, r, sel)
+                    : i == y0 && (Shape::pair_mask & 2) != 0 ? key_big_pair<1>(ga, K, kk, p, r, sel)
+                                                             : key_big_pair<2>(ga, K, kk, p, r, sel);
                 best = min(best, (k & (kKeepReg ? keep_reg : keep)) | (static_cast<uint32_t>(NS + i) + sel));
                 continue;
             }
@@ -442,14 +442,15 @@ __device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists co
                ((Shape::pair_mask & 4) != 0 && i == z0 + 1)) {
                 continue; // the -C sphere of a pair: answered together with its partner
             }
+            float const kb = Shape::uniform_k ? cs.big_geo[0].k : cs.big_geo[i].k;
             if(i < Shape::big_x) {
-                k = key_big_axis<0, Shape::uniform_k>(cs.big_geo[i], p, r);
+                k = key_big_axis<0, Shape::uniform_k>(cs.axis_coef[2 * i], cs.axis_coef[2 * i + 1], kb, p, r);
             }
             else if(i < Shape::big_x + Shape::big_y) {
-                k = key_big_axis<1, Shape::uniform_k>(cs.big_geo[i], p, r);
+                k = key_big_axis<1, Shape::uniform_k>(cs.axis_coef[2 * i], cs.axis_coef[2 * i + 1], kb, p, r);
             }
             else if(i < Shape::big_x + Shape::big_y + Shape::big_z) {
-                k = key_big_axis<2, Shape::uniform_k>(cs.big_geo[i], p, r);
+                k = key_big_axis<2, Shape::uniform_k>(cs.axis_coef[2 * i], cs.axis_coef[2 * i + 1], kb, p, r);
             }
             else if(i < Shape::big_near) {
                 k = key_big<false, kRobust>(cs.big_geo[i], p, r, p.last == NS + i);

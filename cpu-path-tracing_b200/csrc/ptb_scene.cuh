@@ -105,6 +105,10 @@ struct ConstSceneF32
     int pad_[3];
     SmallGeo small_geo[kMaxConstSpheres];
     BigGeo big_geo[kMaxConstSpheres];
+    // The two coefficients an axis sphere's test reads (its one non-zero g component, K), packed back to back in
+    // list order so that the unrolled scan fetches them with 16-byte uniform loads instead of one load each
+    // (ptb_path_f32.cuh: key_big_axis / key_big_pair)
+    alignas(16) float axis_coef[2 * kMaxConstSpheres];
     int order[2 * kMaxConstSpheres]; // list position -> original sphere index
 };
 
