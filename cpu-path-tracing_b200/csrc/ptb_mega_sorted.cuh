@@ -49,7 +49,7 @@ constexpr int kEmissiveBit = 0x100; // in ShadePlanes::b.w next to the reflectio
 
 // Byte layout of one warp's pool: two rings x four planes of float4[kSortedRing]
 //   plane a = origin xyz, len           plane b = direction xyz, slot
-//   plane c = throughput rgb, last      plane d = rng.state, rng.inc, depth | material << 8, -
+//   plane c = throughput rgb, last      plane d = rng.state, rng.inc, depth, material
 constexpr uint32_t kPlaneBytes = kSortedRing * 16u;
 constexpr uint32_t kRingBytes = 4u * kPlaneBytes;
 constexpr uint32_t kPoolBytes = 2u * kRingBytes;  // READY at +0, PARK at +kRingBytes
@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
 
     constexpr uint32_t kFull = 0xffffffffu;
     uint32_t const lane = threadIdx.x & 31u;
-    uint32_t const lt_mask = (1u << lane) - 1u;
+    uint32_t const lane_bit = 1u << lane;
+    uint32_t const lt_mask = lane_bit - 1u;
     uint32_t const ready_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pool)) + (threadIdx.x >> 5) * kPoolBytes;
     uint32_t const park_base = ready_base + kRingBytes;
     float const k_uniform = Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     // lanes of `need` take the oldest READY entries, lowest lane first; returns the new "holds a ray" mask
     auto const pop = [&](uint32_t need) -> uint32_t {
         uint32_t const rank = __popc(need & lt_mask);
-        bool const take = ((need >> lane) & 1u) != 0u && rank < ready_count;
+        bool const take = (need & lane_bit) != 0u && rank < ready_count;
         if(take) {
             uint32_t const rd = ready_base + ((ready_tail + rank * 16u) & kRingMask);
             float4 const ea = lds128(rd);
@@ -188,9 +189,8 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     q.rng.state = __float_as_uint(ed.x);
                     q.rng.inc = __float_as_uint(ed.y);
                     int const last = __float_as_int(ec.w);
-                    int const dm = __float_as_int(ed.z);
-                    int const mat = dm >> 8;
-                    depth1 = (dm & 0xff) + 1; // main.cpp:111 ++depth
+                    int const mat = __float_as_int(ed.w);
+                    depth1 = __float_as_int(ed.z) + 1; // main.cpp:111 ++depth
                     // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6)
                     float4 const sa = shade(0, last);
                     float nx, ny, nz;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
 
         // ================= one bounce: main.cpp:111-155 =========================================================
         bool park = false, ended = false;
-        bool const alive = ((am >> lane) & 1u) != 0u;
+        bool const alive = (am & lane_bit) != 0u;
         int material = 0;
         if(alive) {
             RayTerms const r = ray_terms(p, k_uniform);
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 sts128(w + kPlaneBytes, p.dx, p.dy, p.dz, __uint_as_float(slot));
                 sts128(w + 2u * kPlaneBytes, p.tr, p.tg, p.tb, __int_as_float(p.last));
                 sts128(w + 3u * kPlaneBytes, __uint_as_float(p.rng.state), __uint_as_float(p.rng.inc),
-                       __int_as_float(p.depth | (material << 8)), 0.0f);
+                       __int_as_float(p.depth), __int_as_float(material));
             }
             uint32_t const n = static_cast<uint32_t>(__popc(pm));
             park_head = (park_head + n * 16u) & kRingMask;
