@@ -340,6 +340,7 @@ def main():
     del t0
 
     if rank == 0:
+        jit = r.jit_info()
         peak_tflops = r.measure_fp32_peak()
         ostats, n_spheres = oracle_statistics(scene, width, height)
         if ostats is None:
@@ -368,6 +369,8 @@ def main():
                 "workload": f"{args.config}: {scene} {width}x{height} @ {spp} spp "
                             + (f"(BASELINE.json configs[{int(args.config[1]) - 1}])" if args.config[0] == "C" else "(sandbox/main.cpp, SURVEY 8 f-1)"),
                 "variant": args.variant, "samples_per_subpixel": samps, "spheres": int(len(spheres)),
+                "codegen": ("run-time compiled for this scene (NVRTC, %d ms once)" % jit["compile_ms"]) if jit["last_launch_jit"]
+                else "precompiled",
                 "partition": f"samples of every sub-pixel split over {world} GPU(s); NCCL sum-reduce to rank 0" if world > 1
                 else "single GPU",
                 "l2": "every step zeroes the accumulation buffer (133 MB at 1080p > 126 MB L2) and the kernel's inputs are "

@@ -36,6 +36,8 @@ VARIANT_WAVEFRONT = 0x1
 VARIANT_MEGAKERNEL_SORTED = 0x2
 ACCEL_AUTO = 0x0000
 ACCEL_SCAN = 0x1000
+CODEGEN_AUTO = 0x00000
+CODEGEN_PRECOMPILED = 0x10000
 PRECISION_FP32 = 0x00
 PRECISION_FP64 = 0x10
 INTEGRATOR_PT = 0x000
@@ -111,6 +113,8 @@ _ptb_set_accum_buffer = _sig("ptb_set_accum_buffer", ctypes.c_int, _vp, _vp, _sz
 _ptb_download_accum = _sig("ptb_download_accum", ctypes.c_int, _vp, _vp, _sz)
 _ptb_get_stats = _sig("ptb_get_stats", ctypes.c_int, _vp, ctypes.POINTER(_Stats))
 _ptb_scene_layout = _sig("ptb_scene_layout", ctypes.c_int, _vp, _vp)
+_ptb_jit_info = _sig("ptb_jit_info", ctypes.c_int, _vp, _vp)
+_ptb_jit_last_error = _sig("ptb_jit_last_error", ctypes.c_char_p, _vp)
 _ptb_trace_samples = _sig("ptb_trace_samples", ctypes.c_int, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp,
                           _vp, _vp)
 _ptb_rng_draws = _sig("ptb_rng_draws", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, ctypes.c_int, _vp)
@@ -128,6 +132,7 @@ EXPORTED_SYMBOLS = (
     "ptb_resolve", "ptb_resolve_rgb8", "ptb_resolve_device", "ptb_measure_fp32_peak", "ptb_accum_buffer", "ptb_set_accum_buffer", "ptb_download_accum",
     "ptb_get_stats", "ptb_scene_layout", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
     "ptb_write_ppm", "ptb_write_ppm_smallpt", "ptb_builtin_smallpt_scene", "ptb_set_smallpt_camera",
+    "ptb_jit_info", "ptb_jit_last_error",
 )
 
 
@@ -339,6 +344,14 @@ class Renderer:
         d = dict(zip(keys, [int(v) for v in out]))
         bits = d.pop("bits")
         d["uniform_k"], d["embed_ok"] = bits & 1, (bits >> 1) & 1
+        return d
+
+    def jit_info(self) -> dict:
+        """Run-time code generation of the sorted megakernel (PTB_CODEGEN_AUTO): see ptb_jit_info in ptb200.h."""
+        out = np.zeros(5, dtype=np.int32)
+        self._check(_ptb_jit_info(self._ctx, _ptr(out)))
+        d = dict(zip(("available", "compiled", "failures", "last_launch_jit", "compile_ms"), [int(v) for v in out]))
+        d["last_error"] = (_ptb_jit_last_error(self._ctx) or b"").decode()
         return d
 
     def trace_samples(self, seed, xs, ys, sxs, sys_, samples, flags=PRECISION_FP64):

@@ -6,6 +6,7 @@
 // live context, and ptb_create fails when no CUDA device is usable.
 #include "../../include/ptb200.h"
 #include "ptb_bvh.hpp"
+#include "ptb_jit.hpp"
 #include "ptb_kernels.h"
 #include "ptb_rng.cuh"
 
@@ -72,6 +73,8 @@ struct ptb_context
     // upload, then whichever of the two the previous sorted launch hit more often
     int inline_material = 1;
     unsigned long long seen_diffuse = 0, seen_specular = 0; // counter values already accounted for
+    JitCache jit;                 // run-time compiled, scene-specialised sorted megakernels (ptb_jit.hpp)
+    bool last_launch_jit = false;
     WavefrontBuffers wf{ nullptr, nullptr, nullptr, 0 };
     ptb_stats stats{};
 };
@@ -902,8 +905,10 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     uint32_t const precision = flags & PTB_PRECISION_MASK;
     uint32_t const integrator = flags & PTB_INTEGRATOR_MASK;
     uint32_t const accel = flags & PTB_ACCEL_MASK;
-    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK | PTB_ACCEL_MASK)) != 0 ||
+    uint32_t const codegen = flags & PTB_CODEGEN_MASK;
+    if((flags & ~(PTB_VARIANT_MASK | PTB_PRECISION_MASK | PTB_INTEGRATOR_MASK | PTB_ACCEL_MASK | PTB_CODEGEN_MASK)) != 0 ||
        variant > PTB_VARIANT_MEGAKERNEL_SORTED || (accel != PTB_ACCEL_AUTO && accel != PTB_ACCEL_SCAN) ||
+       (codegen != PTB_CODEGEN_AUTO && codegen != PTB_CODEGEN_PRECOMPILED) ||
        (precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) ||
        (integrator != PTB_INTEGRATOR_PT && integrator != PTB_INTEGRATOR_SMALLPT)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
@@ -936,6 +941,17 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     }
     uint64_t const key = seed_key(seed);
     int launches = 0;
+
+    // Scene-specialised code: compiled (once per scene, ~0.4 s) BEFORE the timed region starts.
+    int sorted_inline = ctx->inline_material;
+    if(char const* force = std::getenv("PTB_INLINE_MATERIAL")) { // experiments (dev/)
+        sorted_inline = std::atoi(force) == 0 ? 0 : 1;
+    }
+    JitKernel const* jit_kernel = nullptr;
+    if(variant == PTB_VARIANT_MEGAKERNEL_SORTED && precision == PTB_PRECISION_FP32 && codegen == PTB_CODEGEN_AUTO &&
+       ctx->n <= kSmemShadeSpheres && megakernel_has_specialisation(ctx->counts)) {
+        jit_kernel = ctx->jit.get(ctx->cs, ctx->counts, sorted_inline);
+    }
 
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     if(precision == PTB_PRECISION_FP64) {
@@ -1004,11 +1020,13 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
             PTB_CUDA(ctx, launch_wavefront(buf, p, ctx->counts, ctx->sm_count, st, &launches));
         }
         else if(variant == PTB_VARIANT_MEGAKERNEL_SORTED) {
-            int inline_material = ctx->inline_material;
-            if(char const* force = std::getenv("PTB_INLINE_MATERIAL")) { // experiments (dev/)
-                inline_material = std::atoi(force) == 0 ? 0 : 1;
+            ctx->last_launch_jit = jit_kernel != nullptr;
+            if(jit_kernel != nullptr) {
+                PTB_CUDA(ctx, ctx->jit.launch(*jit_kernel, p, ctx->cs, ctx->sm_count, st, &launches));
             }
-            PTB_CUDA(ctx, launch_megakernel_sorted(p, ctx->counts, ctx->sm_count, st, &launches, inline_material));
+            else {
+                PTB_CUDA(ctx, launch_megakernel_sorted(p, ctx->counts, ctx->sm_count, st, &launches, sorted_inline));
+            }
         }
         else {
             PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches, smallpt));
@@ -1215,6 +1233,24 @@ int ptb_scene_layout(ptb_context* ctx, int32_t out[10])
                             megakernel_has_specialisation(c) ? 1 : 0 };
     std::memcpy(out, v, sizeof(v));
     return PTB_OK;
+}
+
+int ptb_jit_info(ptb_context* ctx, int32_t out[5])
+{
+    if(ctx == nullptr || out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    out[0] = ctx->jit.available() ? 1 : 0;
+    out[1] = ctx->jit.compiled();
+    out[2] = ctx->jit.failures();
+    out[3] = ctx->last_launch_jit ? 1 : 0;
+    out[4] = static_cast<int32_t>(ctx->jit.compile_ms());
+    return PTB_OK;
+}
+
+char const* ptb_jit_last_error(ptb_context* ctx)
+{
+    return ctx != nullptr ? ctx->jit.last_error().c_str() : "";
 }
 
 int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,

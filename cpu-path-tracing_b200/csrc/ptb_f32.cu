@@ -38,19 +38,6 @@ cudaError_t upload_const_scene(ConstSceneF32 const& cs, cudaStream_t stream)
     return cudaMemcpyToSymbolAsync(c_scene, &cs, sizeof(cs), 0, cudaMemcpyHostToDevice, stream);
 }
 
-__device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z, float w)
-{
-    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
-                 :
-                 : "l"(addr), "f"(x), "f"(y), "f"(z), "f"(w)
-                 : "memory");
-}
-
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
-{
-    return __reduce_add_sync(0xffffffffu, v);
-}
-
 // Per-warp ring of pre-generated camera samples (shared memory).  Generating a primary ray
 // costs ~130 instructions; done in place by the one or two lanes whose path just ended it
 // would issue at <10 % lane utilisation on almost every iteration (measured: 30 % of all

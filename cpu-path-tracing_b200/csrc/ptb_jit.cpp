@@ -1,0 +1,332 @@
+// ptb_jit.cpp -- see ptb_jit.hpp.  Host code only; NVRTC and the driver API are reached through dlopen.
+#include "ptb_jit.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+
+#include <cuda.h>
+#include <nvrtc.h>
+
+// build/ptb_jit_sources.inc (Makefile): kJitHeaderNames[], kJitHeaderSources[], kJitHeaderCount -- the device
+// headers as they were when the library was built
+#include "ptb_jit_sources.inc"
+
+namespace ptb {
+
+namespace {
+
+struct Api
+{
+    void* nvrtc = nullptr;
+    void* cuda = nullptr;
+    // NVRTC
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, char const*, char const*, int, char const* const*, char const* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, char const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, char const* const*) = nullptr;
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, char const*, char const**) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    // driver
+    CUresult (*ModuleLoadData)(CUmodule*, void const*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, char const*) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, char const*) = nullptr;
+    CUresult (*MemcpyHtoDAsync)(CUdeviceptr, void const*, size_t, CUstream) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
+                             void**) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*GetErrorString)(CUresult, char const**) = nullptr;
+    bool ok = false;
+};
+
+template<class F>
+bool sym(void* lib, char const* name, F& out)
+{
+    out = reinterpret_cast<F>(dlsym(lib, name));
+    return out != nullptr;
+}
+
+Api& api()
+{
+    static Api a = [] {
+        Api x;
+        char const* off = std::getenv("PTB_JIT");
+        if(off != nullptr && std::strcmp(off, "0") == 0) {
+            return x;
+        }
+        for(char const* n : { "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so" }) {
+            x.nvrtc = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if(x.nvrtc != nullptr) {
+                break;
+            }
+        }
+        for(char const* n : { "libcuda.so.1", "libcuda.so" }) {
+            x.cuda = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if(x.cuda != nullptr) {
+                break;
+            }
+        }
+        if(x.nvrtc == nullptr || x.cuda == nullptr) {
+            return x;
+        }
+        bool ok = sym(x.nvrtc, "nvrtcCreateProgram", x.CreateProgram) && sym(x.nvrtc, "nvrtcDestroyProgram", x.DestroyProgram) &&
+                  sym(x.nvrtc, "nvrtcAddNameExpression", x.AddNameExpression) && sym(x.nvrtc, "nvrtcCompileProgram", x.CompileProgram) &&
+                  sym(x.nvrtc, "nvrtcGetLoweredName", x.GetLoweredName) && sym(x.nvrtc, "nvrtcGetCUBINSize", x.GetCUBINSize) &&
+                  sym(x.nvrtc, "nvrtcGetCUBIN", x.GetCUBIN) && sym(x.nvrtc, "nvrtcGetProgramLogSize", x.GetProgramLogSize) &&
+                  sym(x.nvrtc, "nvrtcGetProgramLog", x.GetProgramLog);
+        ok = ok && sym(x.cuda, "cuModuleLoadData", x.ModuleLoadData) && sym(x.cuda, "cuModuleUnload", x.ModuleUnload) &&
+             sym(x.cuda, "cuModuleGetFunction", x.ModuleGetFunction) && sym(x.cuda, "cuModuleGetGlobal_v2", x.ModuleGetGlobal) &&
+             sym(x.cuda, "cuMemcpyHtoDAsync_v2", x.MemcpyHtoDAsync) && sym(x.cuda, "cuLaunchKernel", x.LaunchKernel) &&
+             sym(x.cuda, "cuOccupancyMaxActiveBlocksPerMultiprocessor", x.OccupancyMaxActiveBlocks) &&
+             sym(x.cuda, "cuGetErrorString", x.GetErrorString);
+        x.ok = ok;
+        return x;
+    }();
+    return a;
+}
+
+void put_float(std::string& s, float v)
+{
+    char buf[48];
+    std::snprintf(buf, sizeof(buf), "%af", static_cast<double>(v)); // hex float: exact round trip (C++17 literal)
+    s += buf;
+}
+
+int small_count(SceneCounts const& c)
+{
+    return c.small_near + c.small_both;
+}
+int big_count(SceneCounts const& c)
+{
+    return c.big_near + c.big_both;
+}
+
+} // namespace
+
+std::string JitCache::kernel_name(SceneCounts const& c, int inline_material)
+{
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "ptb::mega_sorted_kernel<ptb::SceneShape<%d, %d, %d, %d, %d, %d, %d, %s, %s, %d>, true, %d>", c.small_near,
+                  c.small_both, c.big_near, c.big_both, c.big_x, c.big_y, c.big_z, c.uniform_k ? "true" : "false",
+                  c.embed_ok ? "true" : "false", c.pair_mask, inline_material == 0 ? 0 : 1);
+    return buf;
+}
+
+std::string JitCache::translation_unit(ConstSceneF32 const& cs, SceneCounts const& c)
+{
+    int const ns = small_count(c), nb = big_count(c);
+    std::string init = "{ { ";
+    for(int i = 0; i < (ns > 0 ? ns : 1); ++i) {
+        SmallGeo const g = i < ns ? cs.small_geo[i] : SmallGeo{ 0.0f, 0.0f, 0.0f, 0.0f };
+        init += "{ ";
+        put_float(init, g.cx);
+        init += ", ";
+        put_float(init, g.cy);
+        init += ", ";
+        put_float(init, g.cz);
+        init += ", ";
+        put_float(init, g.r2);
+        init += " }, ";
+    }
+    init += "}, { ";
+    for(int i = 0; i < (nb > 0 ? nb : 1); ++i) {
+        BigGeo const g = i < nb ? cs.big_geo[i] : BigGeo{ 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+        float const f[8] = { g.gx, g.gy, g.gz, g.k, g.K, g.two_r, 0.0f, 0.0f };
+        init += "{ ";
+        for(int k = 0; k < 8; ++k) {
+            put_float(init, f[k]);
+            init += k < 7 ? ", " : " }, ";
+        }
+    }
+    init += "}, { ";
+    for(int i = 0; i < (nb > 0 ? 2 * nb : 2); ++i) {
+        put_float(init, i < 2 * nb ? cs.axis_coef[i] : 0.0f);
+        init += ", ";
+    }
+    init += "}, 0, 0, 0, 0 }";
+
+    std::string tu;
+    tu += "// generated by ptb_jit.cpp: the sorted megakernel with this scene's coefficients as literals\n";
+    tu += "#define PTB_JIT_SCENE_INIT " + init + "\n";
+    tu += "#include \"ptb_kernels.h\"\n#include \"ptb_path_f32.cuh\"\n";
+    tu += "namespace ptb { __constant__ ConstSceneF32 c_scene; }\n";
+    tu += "#include \"ptb_mega_sorted.cuh\"\n";
+    return tu;
+}
+
+bool JitCache::available()
+{
+    if(state_ == 0) {
+        state_ = api().ok ? 1 : -1;
+        if(state_ < 0) {
+            error_ = "run-time compilation unavailable (PTB_JIT=0, or libnvrtc / libcuda not found)";
+        }
+    }
+    return state_ > 0;
+}
+
+JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, int inline_material)
+{
+    if(!available() || !c.fits_const) {
+        return nullptr;
+    }
+    int const ns = small_count(c), nb = big_count(c);
+    // key: layout + in-place material + every coefficient the kernel reads, bit for bit
+    std::vector<uint32_t> key = { static_cast<uint32_t>(c.small_near), static_cast<uint32_t>(c.small_both),
+                                  static_cast<uint32_t>(c.big_near),   static_cast<uint32_t>(c.big_both),
+                                  static_cast<uint32_t>(c.big_x),      static_cast<uint32_t>(c.big_y),
+                                  static_cast<uint32_t>(c.big_z),      static_cast<uint32_t>(c.uniform_k),
+                                  static_cast<uint32_t>(c.embed_ok),   static_cast<uint32_t>(c.pair_mask),
+                                  static_cast<uint32_t>(inline_material == 0 ? 0 : 1) };
+    auto const push = [&](void const* p, size_t bytes) {
+        size_t const n = bytes / sizeof(uint32_t);
+        size_t const at = key.size();
+        key.resize(at + n);
+        std::memcpy(key.data() + at, p, n * sizeof(uint32_t));
+    };
+    push(cs.small_geo, static_cast<size_t>(ns) * sizeof(SmallGeo));
+    push(cs.big_geo, static_cast<size_t>(nb) * sizeof(BigGeo));
+    push(cs.axis_coef, static_cast<size_t>(2 * nb) * sizeof(float));
+    auto it = cache_.find(key);
+    if(it != cache_.end()) {
+        return it->second.failed ? nullptr : &it->second;
+    }
+
+    Api& a = api();
+    JitKernel k;
+    auto const t0 = std::chrono::steady_clock::now();
+    std::string const tu = translation_unit(cs, c);
+    std::string const name = kernel_name(c, inline_material);
+    nvrtcProgram prog = nullptr;
+    auto const fail = [&](std::string const& what) -> JitKernel const* {
+        error_ = what;
+        failures_++;
+        if(prog != nullptr) {
+            a.DestroyProgram(&prog);
+        }
+        if(k.module != nullptr) {
+            a.ModuleUnload(static_cast<CUmodule>(k.module));
+        }
+        JitKernel bad;
+        bad.failed = true;
+        cache_[key] = bad;
+        return nullptr;
+    };
+    if(a.CreateProgram(&prog, tu.c_str(), "ptb_jit_tu.cu", kJitHeaderCount, kJitHeaderSources, kJitHeaderNames) != NVRTC_SUCCESS) {
+        return fail("nvrtcCreateProgram failed");
+    }
+    std::string const var = "&ptb::c_scene";
+    if(a.AddNameExpression(prog, name.c_str()) != NVRTC_SUCCESS || a.AddNameExpression(prog, var.c_str()) != NVRTC_SUCCESS) {
+        return fail("nvrtcAddNameExpression failed");
+    }
+    char const* opts[] = { "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo" };
+    nvrtcResult const rc = a.CompileProgram(prog, 3, opts);
+    if(rc != NVRTC_SUCCESS) {
+        size_t n = 0;
+        a.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if(n > 1) {
+            a.GetProgramLog(prog, &log[0]);
+        }
+        return fail("nvrtcCompileProgram failed: " + log.substr(0, 2000));
+    }
+    char const* lowered_fn = nullptr;
+    char const* lowered_var = nullptr;
+    if(a.GetLoweredName(prog, name.c_str(), &lowered_fn) != NVRTC_SUCCESS || a.GetLoweredName(prog, var.c_str(), &lowered_var) != NVRTC_SUCCESS) {
+        return fail("nvrtcGetLoweredName failed for " + name);
+    }
+    size_t bytes = 0;
+    if(a.GetCUBINSize(prog, &bytes) != NVRTC_SUCCESS || bytes == 0) {
+        return fail("nvrtcGetCUBINSize failed");
+    }
+    std::vector<char> cubin(bytes);
+    if(a.GetCUBIN(prog, cubin.data()) != NVRTC_SUCCESS) {
+        return fail("nvrtcGetCUBIN failed");
+    }
+    auto const cu_fail = [&](char const* what, CUresult e) {
+        char const* s = nullptr;
+        a.GetErrorString(e, &s);
+        return fail(std::string(what) + ": " + (s != nullptr ? s : "unknown driver error"));
+    };
+    CUmodule mod = nullptr;
+    CUresult e = a.ModuleLoadData(&mod, cubin.data());
+    if(e != CUDA_SUCCESS) {
+        return cu_fail("cuModuleLoadData", e);
+    }
+    k.module = mod;
+    CUfunction fn = nullptr;
+    if((e = a.ModuleGetFunction(&fn, mod, lowered_fn)) != CUDA_SUCCESS) {
+        return cu_fail("cuModuleGetFunction", e);
+    }
+    CUdeviceptr dptr = 0;
+    size_t dbytes = 0;
+    if((e = a.ModuleGetGlobal(&dptr, &dbytes, mod, lowered_var)) != CUDA_SUCCESS) {
+        return cu_fail("cuModuleGetGlobal", e);
+    }
+    if(dbytes != sizeof(ConstSceneF32)) {
+        return fail("the compiled module's c_scene has an unexpected size");
+    }
+    int per_sm = 0;
+    if((e = a.OccupancyMaxActiveBlocks(&per_sm, fn, 128, 0)) != CUDA_SUCCESS) {
+        return cu_fail("cuOccupancyMaxActiveBlocksPerMultiprocessor", e);
+    }
+    a.DestroyProgram(&prog);
+    prog = nullptr;
+    k.function = fn;
+    k.c_scene = dptr;
+    k.c_scene_bytes = dbytes;
+    k.blocks_per_sm = per_sm < 1 ? 1 : per_sm;
+    compile_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    compiled_++;
+    auto const ins = cache_.emplace(std::move(key), k);
+    return &ins.first->second;
+}
+
+cudaError_t JitCache::launch(JitKernel const& k, RenderParamsF32 const& p, ConstSceneF32 const& cs, int sm_count, cudaStream_t stream,
+                             int* launches)
+{
+    Api& a = api();
+    cudaError_t ce = cudaMemsetAsync(&p.counters->tile_cursor, 0, sizeof(unsigned long long), stream);
+    if(ce != cudaSuccess) {
+        return ce;
+    }
+    // camera and the rest of the constant block of THIS module (the coefficients in it are not read by the kernel)
+    if(a.MemcpyHtoDAsync(static_cast<CUdeviceptr>(k.c_scene), &cs, sizeof(ConstSceneF32), reinterpret_cast<CUstream>(stream)) != CUDA_SUCCESS) {
+        return cudaErrorUnknown;
+    }
+    unsigned long long blocks = static_cast<unsigned long long>(sm_count) * static_cast<unsigned long long>(k.blocks_per_sm);
+    unsigned long long const needed = (static_cast<unsigned long long>(p.ntiles) + 3ull) / 4ull; // 4 warps per block
+    blocks = blocks > needed ? needed : blocks;
+    blocks = blocks < 1 ? 1 : blocks;
+    RenderParamsF32 params = p;
+    void* args[] = { &params };
+    if(a.LaunchKernel(static_cast<CUfunction>(k.function), static_cast<unsigned>(blocks), 1, 1, 128, 1, 1, 0, reinterpret_cast<CUstream>(stream),
+                      args, nullptr) != CUDA_SUCCESS) {
+        return cudaErrorLaunchFailure;
+    }
+    if(launches != nullptr) {
+        *launches += 1;
+    }
+    return cudaSuccess;
+}
+
+JitCache::~JitCache()
+{
+    Api& a = api();
+    if(!a.ok) {
+        return;
+    }
+    for(auto& kv : cache_) {
+        if(kv.second.module != nullptr) {
+            a.ModuleUnload(static_cast<CUmodule>(kv.second.module));
+        }
+    }
+}
+
+} // namespace ptb

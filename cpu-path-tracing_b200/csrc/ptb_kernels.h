@@ -2,9 +2,7 @@
 // internal to libptb200.so; the public surface is include/ptb200.h).
 #pragma once
 
-#include <cstddef>
-#include <cstdint>
-#include <cuda_runtime.h>
+#include "ptb_types.h"
 
 #include "ptb_scene.cuh"
 
@@ -40,6 +38,8 @@ struct RenderParamsF32
     int n_total;
     uint32_t key_mask;      // ~(2^kIdBits - 1), handed over as DATA so that it lives in a register (see closest_hit)
 };
+
+#ifndef __CUDACC_RTC__ // everything below is host-side; the run-time compiler only needs the records above
 
 // Copy the packed scene into the constant bank the FP32 kernels read.
 cudaError_t upload_const_scene(ConstSceneF32 const& cs, cudaStream_t stream);
@@ -131,5 +131,7 @@ cudaError_t launch_fp32_peak(int sm_count, int iters, float* scratch, cudaStream
 // ---- stream check ---------------------------------------------------------------------------------------------
 cudaError_t launch_rng_draws(uint64_t key, uint32_t const* slot, uint32_t const* sample, uint32_t count, int n_draws,
                              double* out, cudaStream_t stream);
+
+#endif // __CUDACC_RTC__
 
 } // namespace ptb

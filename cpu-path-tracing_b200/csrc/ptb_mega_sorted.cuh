@@ -104,7 +104,21 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     uint32_t const lt_mask = lane_bit - 1u;
     uint32_t const ready_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pool)) + (threadIdx.x >> 5) * kPoolBytes;
     uint32_t const park_base = ready_base + kRingBytes;
-    float const k_uniform = Shape::uniform_k ? c_scene.big_geo[0].k : 0.0f;
+#ifdef PTB_JIT_SCENE_INIT
+    // Run-time compiled build (ptb_jit.cpp): the scene's coefficients arrive as LITERALS and fold into immediates of
+    // the FFMA / FADD instructions -- no uniform loads in the scan, no register-file bandwidth for them either.
+    struct JitScene
+    {
+        SmallGeo small_geo[Shape::small_near + Shape::small_both > 0 ? Shape::small_near + Shape::small_both : 1];
+        BigGeo big_geo[Shape::big_near + Shape::big_both > 0 ? Shape::big_near + Shape::big_both : 1];
+        float axis_coef[Shape::big_near + Shape::big_both > 0 ? 2 * (Shape::big_near + Shape::big_both) : 2];
+        int n_small_near, n_small, n_big_near, n_big; // never read: specialised shapes carry their counts as types
+    };
+    JitScene const scene = PTB_JIT_SCENE_INIT;
+#else
+    ConstSceneF32 const& scene = c_scene;
+#endif
+    float const k_uniform = Shape::uniform_k ? scene.big_geo[0].k : 0.0f;
     uint32_t const keep_reg = prm.key_mask; // see closest_hit: a run-time value so that it stays in a register
 
     // warp-uniform state; ring positions are BYTE offsets inside a plane (multiples of 16, wrapped with kRingMask)
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
             RayTerms const r = ray_terms(p, k_uniform);
             float t;
             int id;
-            bool const hit = closest_hit<Shape, true>(c_scene, prm.geo, p, r, t, id, keep_reg);
+            bool const hit = closest_hit<Shape, true>(scene, prm.geo, p, r, t, id, keep_reg);
             cnt.rays++;
             if(!hit) {
                 // main.cpp:116-119 sky gradient on the unit direction; the path ends
@@ -380,6 +394,8 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     }
 }
 
+#ifndef __CUDACC_RTC__ // host side: launchers of the precompiled instantiations
+
 template<class Shape, bool kSmem, int kInline>
 static cudaError_t launch_sorted_one(RenderParamsF32 const& p, int sm_count, cudaStream_t stream)
 {
@@ -433,5 +449,7 @@ cudaError_t launch_megakernel_sorted(RenderParamsF32 const& p, SceneCounts const
     }
     return inline_material == 0 ? launch_sorted_inline<0>(p, c, sm_count, stream) : launch_sorted_inline<1>(p, c, sm_count, stream);
 }
+
+#endif // __CUDACC_RTC__
 
 } // namespace ptb

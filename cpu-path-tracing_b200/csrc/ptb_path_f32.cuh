@@ -60,6 +60,21 @@ __device__ __forceinline__ float fast_rsqrt(float x)
     return r;
 }
 
+// ---- small device utilities shared by the kernels ------------------------------------------------------------------
+// One 16-byte vector reduction into a slot of the accumulation buffer (sm_90+): no read-modify-write.
+__device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z, float w)
+{
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :
+                 : "l"(addr), "f"(x), "f"(y), "f"(z), "f"(w)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+    return __reduce_add_sync(0xffffffffu, v);
+}
+
 struct PathF32
 {
     float ox, oy, oz; // ray origin (shifted frame)
@@ -397,8 +412,8 @@ using GenericShape = SceneShape<-1, -1, -1, -1>;
 // kKeepReg: the mantissa mask comes in a REGISTER (keep_reg, loaded once per kernel through an opaque move) so
 // that "(key & mask) | position" is a single three-input LOP3 with the position as its immediate; with both as
 // immediates the compiler needs two LOP3 per sphere.
-template<class Shape, bool kKeepReg = false>
-__device__ __forceinline__ bool closest_hit(ConstSceneF32 const& cs, GeoLists const& gl, PathF32 const& p,
+template<class Shape, bool kKeepReg = false, class Scene = ConstSceneF32>
+__device__ __forceinline__ bool closest_hit(Scene const& cs, GeoLists const& gl, PathF32 const& p,
                                             RayTerms const& r, float& t_out, int& id_out, uint32_t keep_reg = 0u)
 {
     uint32_t best = kNoHitBits;

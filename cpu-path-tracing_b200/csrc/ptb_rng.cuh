@@ -11,7 +11,7 @@
 // (0x3f800000 | r>>9) - 1, a 23-bit value exact in binary32 and binary64 alike.
 #pragma once
 
-#include <cstdint>
+#include "ptb_types.h"
 
 namespace ptb {
 

@@ -26,8 +26,7 @@
 //     planes), `order[]` maps a list position back to the caller's sphere index.
 #pragma once
 
-#include <cstdint>
-#include <cuda_runtime.h>
+#include "ptb_types.h"
 
 namespace ptb {
 

@@ -341,6 +341,61 @@ def test_full_size_box_mirror_properties(gpu, oracle_port):
     assert abs(small[dark].mean() - ref[dark].mean()) < 0.005
 
 
+# ---- run-time specialised code (PTB_CODEGEN_AUTO) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SCENES)
+def test_runtime_compiled_kernel_is_the_precompiled_kernel(gpu, name):
+    """The sorted megakernel compiled at run time for THIS scene (sphere coefficients as immediates) traces the very
+    paths of the precompiled constant-bank kernel; it is compiled once per scene and reused."""
+    W, H, S = 192, 108, 10
+    sph, cfg = gpu.builtin_scene(name, W, H)
+    cam = gpu.camera_with_config(cfg)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        info0 = r.jit_info()
+        if not info0["available"]:
+            pytest.skip("libnvrtc / libcuda not available: " + info0["last_error"])
+        r.render(31, 0, S, flags | gpu.CODEGEN_PRECOMPILED)
+        assert r.jit_info()["last_launch_jit"] == 0
+        pre, st_p = r.download_accum(), r.stats()
+        r.clear()
+        r.render(31, 0, S, flags | gpu.CODEGEN_AUTO)
+        info = r.jit_info()
+        assert info["failures"] == 0, info["last_error"]
+        assert info["last_launch_jit"] == 1 and info["compiled"] >= 1
+        jit, st_j = r.download_accum(), r.stats()
+        r.upload_scene(sph)  # same numbers again: the cache must answer
+        r.set_camera(cam)
+        r.render(31, S, S, flags)
+        assert r.jit_info()["compiled"] == info["compiled"]
+    assert np.all(pre[:, 3] == S) and np.all(jit[:, 3] == S)
+    assert (st_j.rays, st_j.hits_diffuse, st_j.hits_specular, st_j.hits_dielectric) == \
+        (st_p.rays, st_p.hits_diffuse, st_p.hits_specular, st_p.hits_dielectric)
+    assert np.isclose(pre[:, :3], jit[:, :3], rtol=1e-5, atol=1e-5).all()
+
+
+def test_runtime_compilation_follows_the_scene(gpu):
+    """Different coefficients -> a different kernel; a scene without a specialised layout -> the precompiled path."""
+    W, H = 64, 36
+    sph, cfg = gpu.builtin_scene("box_mirror", W, H)
+    cam = gpu.camera_with_config(cfg)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        if not r.jit_info()["available"]:
+            pytest.skip("run-time compilation not available")
+        r.render(1, 0, 2, flags)
+        n1 = r.jit_info()["compiled"]
+        moved = sph.copy()
+        moved["position"][6][0] += 0.01  # nudge the mirror ball
+        r.upload_scene(moved)
+        r.render(1, 0, 2, flags)
+        assert r.jit_info()["compiled"] == n1 + 1 and r.jit_info()["last_launch_jit"] == 1
+        big, cfg2 = gpu.builtin_scene("spheres10k", W, H)
+        r.upload_scene(big)
+        r.set_camera(gpu.camera_with_config(cfg2))
+        r.render(1, 0, 1, flags)
+        assert r.jit_info()["last_launch_jit"] == 0 and r.jit_info()["failures"] == 0
+
+
 # ---- degenerate scenes ----------------------------------------------------------------------------------------------------
 def test_empty_scene_is_all_sky(gpu, oracle_port):
     """No spheres: every ray misses (main.cpp:114-120).  FP64 equals the oracle to rounding, every FP32 variant agrees."""
@@ -540,7 +595,7 @@ def test_error_behaviour(gpu):
             r.set_image(0, 8, 2)
         r.set_image(8, 8, 2)
         with pytest.raises(gpu.PtbError) as e:
-            r.render(1, 0, 1, 0x10000)  # unknown flag
+            r.render(1, 0, 1, 0x100000)  # unknown flag
         assert e.value.code == -1
         with pytest.raises(gpu.PtbError):
             r.render(1, 0xFFFFFFFF, 2)  # sample range overflow
