@@ -948,9 +948,17 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         sorted_inline = std::atoi(force) == 0 ? 0 : 1;
     }
     JitKernel const* jit_kernel = nullptr;
-    if(variant == PTB_VARIANT_MEGAKERNEL_SORTED && precision == PTB_PRECISION_FP32 && codegen == PTB_CODEGEN_AUTO &&
-       ctx->n <= kSmemShadeSpheres && megakernel_has_specialisation(ctx->counts)) {
-        jit_kernel = ctx->jit.get(ctx->cs, ctx->counts, sorted_inline);
+    // Any layout that fits the unrolled scan qualifies, not only the ones the library ships precompiled: a scene of up to
+    // 16 spheres (32 when the index cannot ride in the key) that has no precompiled specialisation would otherwise take
+    // the run-time-count kernel.
+    {
+        SceneCounts const& c = ctx->counts;
+        int const total = c.small_near + c.small_both + c.big_near + c.big_both;
+        bool const unrollable = c.fits_const && total >= 1 && total <= (c.embed_ok ? 16 : 32);
+        if(variant == PTB_VARIANT_MEGAKERNEL_SORTED && precision == PTB_PRECISION_FP32 && codegen == PTB_CODEGEN_AUTO &&
+           ctx->n <= kSmemShadeSpheres && unrollable) {
+            jit_kernel = ctx->jit.get(ctx->cs, ctx->counts, sorted_inline);
+        }
     }
 
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));

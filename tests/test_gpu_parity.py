@@ -373,6 +373,35 @@ def test_runtime_compiled_kernel_is_the_precompiled_kernel(gpu, name):
     assert np.isclose(pre[:, :3], jit[:, :3], rtol=1e-5, atol=1e-5).all()
 
 
+def test_runtime_compilation_specialises_layouts_the_library_does_not_ship(gpu, oracle_port):
+    """box_mirror plus two more balls has no precompiled unrolled kernel (it would take the run-time-count scan);
+    compiled at run time it gets one.  Both agree with the FP64 oracle and with each other."""
+    W, H, S = 160, 90, 8
+    sph, cfg = gpu.builtin_scene("box_mirror", W, H)
+    cam = gpu.camera_with_config(cfg)
+    extra = sph[6:8].copy()  # a second mirror ball and a second glass ball, higher up
+    extra["position"][:, 1] += 0.35
+    extra["position"][:, 2] -= 0.15
+    scene = np.concatenate([sph, extra])
+    ref = oracle_port.render(scene, cam, W, H, S, 2, 13, 0)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, scene, cam, W, H) as r:
+        if not r.jit_info()["available"]:
+            pytest.skip("run-time compilation not available")
+        assert r.scene_layout()["specialised"] == 0
+        r.render(13, 0, S, flags | gpu.CODEGEN_PRECOMPILED)
+        pre, img_pre, st_p = r.download_accum(), r.resolve(), r.stats()
+        r.clear()
+        r.render(13, 0, S, flags)
+        info = r.jit_info()
+        assert info["failures"] == 0 and info["last_launch_jit"] == 1, info["last_error"]
+        jit, img_jit, st_j = r.download_accum(), r.resolve(), r.stats()
+    assert np.all(pre[:, 3] == S) and np.all(jit[:, 3] == S) and np.isfinite(jit).all()
+    assert abs(st_j.rays - st_p.rays) <= 2e-3 * st_p.rays  # different FP32 root formulas: a few chaotic paths differ
+    assert np.abs(img_pre - ref).mean() < 2e-3 and np.abs(img_jit - ref).mean() < 2e-3
+    assert (np.abs(img_jit - ref) < 1e-4).mean() > 0.8
+
+
 def test_runtime_compilation_follows_the_scene(gpu):
     """Different coefficients -> a different kernel; a scene without a specialised layout -> the precompiled path."""
     W, H = 64, 36
