@@ -171,7 +171,7 @@ bool JitCache::available()
     return state_ > 0;
 }
 
-JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, int inline_material)
+JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, int inline_material, bool eager)
 {
     if(!available() || !c.fits_const) {
         return nullptr;
@@ -193,9 +193,34 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, in
     push(cs.small_geo, static_cast<size_t>(ns) * sizeof(SmallGeo));
     push(cs.big_geo, static_cast<size_t>(nb) * sizeof(BigGeo));
     push(cs.axis_coef, static_cast<size_t>(2 * nb) * sizeof(float));
+    ++clock_;
     auto it = cache_.find(key);
-    if(it != cache_.end()) {
+    if(it != cache_.end() && !it->second.pending) {
+        it->second.last_use = clock_;
         return it->second.failed ? nullptr : &it->second;
+    }
+    if(it == cache_.end() && !eager) {
+        JitKernel seen;
+        seen.pending = true;
+        seen.last_use = clock_;
+        cache_[key] = seen; // compile when it comes back
+        return nullptr;
+    }
+    if(it != cache_.end()) {
+        cache_.erase(it);
+    }
+    // room: unload the least recently used module
+    while(cache_.size() >= kMaxModules) {
+        auto victim = cache_.begin();
+        for(auto j = cache_.begin(); j != cache_.end(); ++j) {
+            if(j->second.last_use < victim->second.last_use) {
+                victim = j;
+            }
+        }
+        if(victim->second.module != nullptr) {
+            api().ModuleUnload(static_cast<CUmodule>(victim->second.module));
+        }
+        cache_.erase(victim);
     }
 
     Api& a = api();
@@ -215,6 +240,7 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, in
         }
         JitKernel bad;
         bad.failed = true;
+        bad.last_use = clock_;
         cache_[key] = bad;
         return nullptr;
     };
@@ -282,6 +308,7 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, in
     k.c_scene = dptr;
     k.c_scene_bytes = dbytes;
     k.blocks_per_sm = per_sm < 1 ? 1 : per_sm;
+    k.last_use = clock_;
     compile_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     compiled_++;
     auto const ins = cache_.emplace(std::move(key), k);

@@ -30,6 +30,8 @@ struct JitKernel
     size_t c_scene_bytes = 0;
     int blocks_per_sm = 0;
     bool failed = false;             // negative cache entry: do not try this key again
+    bool pending = false;            // seen once, not compiled yet
+    unsigned long long last_use = 0;
 };
 
 class JitCache
@@ -40,8 +42,12 @@ public:
     JitCache& operator=(JitCache const&) = delete;
     ~JitCache();
 
-    // The specialised kernel for this packed scene, compiled on first use; nullptr = use the precompiled kernel.
-    JitKernel const* get(ConstSceneF32 const& cs, SceneCounts const& counts, int inline_material);
+    // The specialised kernel for this packed scene; nullptr = use the precompiled kernel.  Compiling costs ~0.2-0.4 s,
+    // so it has to be worth it: `eager` (the caller is about to trace enough paths to amortise it) compiles at once,
+    // otherwise a scene is compiled the SECOND time it is asked for -- geometry that changes every frame never is.
+    // At most kMaxModules stay loaded (least recently used goes first).
+    static constexpr size_t kMaxModules = 32;
+    JitKernel const* get(ConstSceneF32 const& cs, SceneCounts const& counts, int inline_material, bool eager);
     // Launch it: same grid policy and semantics as launch_megakernel_sorted.
     cudaError_t launch(JitKernel const& k, RenderParamsF32 const& p, ConstSceneF32 const& cs, int sm_count, cudaStream_t stream,
                        int* launches);
@@ -62,6 +68,7 @@ private:
     double compile_ms_ = 0.0;
     std::string error_;
     int state_ = 0; // 0 unknown, 1 available, -1 unavailable
+    unsigned long long clock_ = 0;
 };
 
 } // namespace ptb

@@ -359,9 +359,13 @@ def test_runtime_compiled_kernel_is_the_precompiled_kernel(gpu, name):
         pre, st_p = r.download_accum(), r.stats()
         r.clear()
         r.render(31, 0, S, flags | gpu.CODEGEN_AUTO)
+        # a small job does not pay for a compilation the first time a scene shows up ...
+        assert r.jit_info()["last_launch_jit"] == 0 and r.jit_info()["compiled"] == info0["compiled"]
+        r.clear()
+        r.render(31, 0, S, flags | gpu.CODEGEN_AUTO)  # ... the second time it does
         info = r.jit_info()
         assert info["failures"] == 0, info["last_error"]
-        assert info["last_launch_jit"] == 1 and info["compiled"] >= 1
+        assert info["last_launch_jit"] == 1 and info["compiled"] == info0["compiled"] + 1
         jit, st_j = r.download_accum(), r.stats()
         r.upload_scene(sph)  # same numbers again: the cache must answer
         r.set_camera(cam)
@@ -393,6 +397,8 @@ def test_runtime_compilation_specialises_layouts_the_library_does_not_ship(gpu, 
         pre, img_pre, st_p = r.download_accum(), r.resolve(), r.stats()
         r.clear()
         r.render(13, 0, S, flags)
+        r.clear()
+        r.render(13, 0, S, flags)  # second sight of the scene: compiled
         info = r.jit_info()
         assert info["failures"] == 0 and info["last_launch_jit"] == 1, info["last_error"]
         jit, img_jit, st_j = r.download_accum(), r.resolve(), r.stats()
@@ -412,11 +418,16 @@ def test_runtime_compilation_follows_the_scene(gpu):
         if not r.jit_info()["available"]:
             pytest.skip("run-time compilation not available")
         r.render(1, 0, 2, flags)
+        r.render(1, 2, 2, flags)
         n1 = r.jit_info()["compiled"]
+        assert n1 >= 1 and r.jit_info()["last_launch_jit"] == 1
         moved = sph.copy()
-        moved["position"][6][0] += 0.01  # nudge the mirror ball
-        r.upload_scene(moved)
-        r.render(1, 0, 2, flags)
+        for step in range(3):  # geometry that changes on every upload is never compiled ...
+            moved["position"][6][0] += 0.01  # nudge the mirror ball
+            r.upload_scene(moved)
+            r.render(1, 0, 2, flags)
+            assert r.jit_info()["compiled"] == n1 and r.jit_info()["last_launch_jit"] == 0
+        r.render(1, 2, 2, flags)  # ... until it stays
         assert r.jit_info()["compiled"] == n1 + 1 and r.jit_info()["last_launch_jit"] == 1
         big, cfg2 = gpu.builtin_scene("spheres10k", W, H)
         r.upload_scene(big)
