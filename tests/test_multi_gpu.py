@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_path):
     cam = pkg.camera_with_config(cfg)
     dr = DistributedRenderer(pkg, rank, rank, world)
     dr.setup(sph, cam, W, H, 2)
-    dr.step(5, S)
+    dr.step(5, S, pkg.PRECISION_FP32 | pkg.VARIANT_MEGAKERNEL_SORTED)  # the product path
     torch.cuda.synchronize()
     if rank == 0:
         np.save(out_path, dr.accum.cpu().numpy())
@@ -52,7 +52,7 @@ def test_two_gpus_match_one(gpu, tmp_path):
         r.upload_scene(sph)
         r.set_camera(cam)
         r.set_image(W, H, 2)
-        r.render(5, 0, S)
+        r.render(5, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
         acc1 = r.download_accum()
     assert np.all(acc2[:, 3] == S) and np.all(acc1[:, 3] == S)
     assert np.allclose(acc1[:, :3], acc2[:, :3], rtol=1e-5, atol=1e-5)
