@@ -408,6 +408,29 @@ def test_runtime_compilation_specialises_layouts_the_library_does_not_ship(gpu, 
     assert (np.abs(img_jit - ref) < 1e-4).mean() > 0.8
 
 
+@pytest.mark.parametrize("refl", [0, 1, 2])
+def test_runtime_compilation_of_a_one_sphere_scene(gpu, oracle_port, refl):
+    """The smallest layouts (one small sphere, no big one; near-only or both-roots list alone)."""
+    W, H, S = 64, 36, 6
+    sph, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    one = sph[1:2].copy()
+    one["reflection"][0] = refl
+    ref = oracle_port.render(one, cam, W, H, S, 2, 6, 0)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, one, cam, W, H) as r:
+        if not r.jit_info()["available"]:
+            pytest.skip("run-time compilation not available")
+        r.render(6, 0, S, flags)
+        r.clear()
+        r.render(6, 0, S, flags)
+        info = r.jit_info()
+        assert info["failures"] == 0 and info["last_launch_jit"] == 1, info["last_error"]
+        acc = r.download_accum()
+        assert np.all(acc[:, 3] == S) and np.isfinite(acc).all()
+        assert np.abs(r.resolve() - ref).mean() < 2e-3
+
+
 def test_runtime_compilation_follows_the_scene(gpu):
     """Different coefficients -> a different kernel; a scene without a specialised layout -> the precompiled path."""
     W, H = 64, 36
