@@ -153,11 +153,12 @@ def test_fp32_image_against_oracle_same_seed(gpu, oracle_port, name, variant):
     assert abs(st.rays / st.paths - {"simple": 2.09, "box": 12.33, "box_mirror": 12.33, "dof_glass": 2.1}[name]) < 0.25
 
 
-def test_fp32_image_rmse_within_monte_carlo_noise(gpu, oracle_port):
+@pytest.mark.parametrize("name", ["box", "box_mirror", "dof_glass"])
+def test_fp32_image_rmse_within_monte_carlo_noise(gpu, oracle_port, name):
     """Independent seeds: RMSE(GPU, reference mean) within the Monte-Carlo bound estimated from K reference renders
     ('Image RMSE')."""
     W, H, S, K = 96, 72, 8, 6
-    sph, cfg = gpu.builtin_scene("box", W, H)
+    sph, cfg = gpu.builtin_scene(name, W, H)
     cam = gpu.camera_with_config(cfg)
     refs = np.stack([oracle_port.render(sph, cam, W, H, S, 2, 1000 + k, 0) for k in range(K)])
     mean_ref, var_px = refs.mean(axis=0), refs.var(axis=0, ddof=1)
