@@ -311,8 +311,13 @@ __device__ __forceinline__ uint32_t key_big_pair(float ga, float K, float k, Pat
 __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 const& p, RayTerms const& r, uint32_t& best,
                                                 int& id)
 {
-    // slab test as (plane - o) * (1 / d): a zero component gives +-inf, 0 * inf = NaN is dropped by fminf / fmaxf
-    float const ix = fast_rcp(p.dx), iy = fast_rcp(p.dy), iz = fast_rcp(p.dz);
+    // slab test t = plane * (1/d) - o * (1/d), one FFMA per plane.  Against (plane - o) * (1/d) the rounding of o * (1/d)
+    // moves t by up to 6e-8 |o| in space units -- the boxes are padded by 1e-6 |c| + 1e-5 for exactly that (ptb_bvh.hpp).
+    // A zero direction component must not become inf (inf - inf): |d_a| is floored at 1e-20, which keeps both plane
+    // distances finite and of the right signs (+-1e20 scale: "never reached" or "always inside").
+    auto const safe_rcp = [](float d) { return fast_rcp(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); };
+    float const ix = safe_rcp(p.dx), iy = safe_rcp(p.dy), iz = safe_rcp(p.dz);
+    float const nx = -p.ox * ix, ny = -p.oy * iy, nz = -p.oz * iz;
     float tbest = best < kNoHitBits ? __uint_as_float(best) + r.eps : 3.0e38f;
     int stack[kBvhStack];
     int sp = 0;
@@ -323,12 +328,12 @@ __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 cons
             float4 const n1 = gl.bvh_nodes[4 * node + 1];
             float4 const n2 = gl.bvh_nodes[4 * node + 2];
             float4 const n3 = gl.bvh_nodes[4 * node + 3];
-            float const ax0 = (n0.x - p.ox) * ix, ax1 = (n0.y - p.ox) * ix;
-            float const ay0 = (n0.z - p.oy) * iy, ay1 = (n0.w - p.oy) * iy;
-            float const az0 = (n2.x - p.oz) * iz, az1 = (n2.y - p.oz) * iz;
-            float const bx0 = (n1.x - p.ox) * ix, bx1 = (n1.y - p.ox) * ix;
-            float const by0 = (n1.z - p.oy) * iy, by1 = (n1.w - p.oy) * iy;
-            float const bz0 = (n2.z - p.oz) * iz, bz1 = (n2.w - p.oz) * iz;
+            float const ax0 = fmaf(n0.x, ix, nx), ax1 = fmaf(n0.y, ix, nx);
+            float const ay0 = fmaf(n0.z, iy, ny), ay1 = fmaf(n0.w, iy, ny);
+            float const az0 = fmaf(n2.x, iz, nz), az1 = fmaf(n2.y, iz, nz);
+            float const bx0 = fmaf(n1.x, ix, nx), bx1 = fmaf(n1.y, ix, nx);
+            float const by0 = fmaf(n1.z, iy, ny), by1 = fmaf(n1.w, iy, ny);
+            float const bz0 = fmaf(n2.z, iz, nz), bz1 = fmaf(n2.w, iz, nz);
             float const amin = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
             float const amax = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tbest));
             float const bmin = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));

@@ -66,7 +66,9 @@ void traverse(std::vector<BvhSphere> const& s, BvhTree const& t, Ray const& r, u
 {
     best = kNoHit;
     id = -1;
-    float const ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
+    auto const safe_rcp = [](float d) { return 1.0f / (std::fabs(d) > 1e-20f ? d : std::copysign(1e-20f, d)); };
+    float const ix = safe_rcp(r.dx), iy = safe_rcp(r.dy), iz = safe_rcp(r.dz);
+    float const nx = -r.ox * ix, ny = -r.oy * iy, nz = -r.oz * iz; // t = plane * (1/d) - o * (1/d), as on the device
     float tbest = 3.0e38f;
     int stack[64];
     int sp = 0;
@@ -75,12 +77,12 @@ void traverse(std::vector<BvhSphere> const& s, BvhTree const& t, Ray const& r, u
         if(node >= 0) {
             ++g_nodes;
             ptb::BvhNode64 const& n = t.nodes[static_cast<size_t>(node)];
-            float const ax0 = (n.n0[0] - r.ox) * ix, ax1 = (n.n0[1] - r.ox) * ix;
-            float const ay0 = (n.n0[2] - r.oy) * iy, ay1 = (n.n0[3] - r.oy) * iy;
-            float const az0 = (n.n2[0] - r.oz) * iz, az1 = (n.n2[1] - r.oz) * iz;
-            float const bx0 = (n.n1[0] - r.ox) * ix, bx1 = (n.n1[1] - r.ox) * ix;
-            float const by0 = (n.n1[2] - r.oy) * iy, by1 = (n.n1[3] - r.oy) * iy;
-            float const bz0 = (n.n2[2] - r.oz) * iz, bz1 = (n.n2[3] - r.oz) * iz;
+            float const ax0 = std::fmaf(n.n0[0], ix, nx), ax1 = std::fmaf(n.n0[1], ix, nx);
+            float const ay0 = std::fmaf(n.n0[2], iy, ny), ay1 = std::fmaf(n.n0[3], iy, ny);
+            float const az0 = std::fmaf(n.n2[0], iz, nz), az1 = std::fmaf(n.n2[1], iz, nz);
+            float const bx0 = std::fmaf(n.n1[0], ix, nx), bx1 = std::fmaf(n.n1[1], ix, nx);
+            float const by0 = std::fmaf(n.n1[2], iy, ny), by1 = std::fmaf(n.n1[3], iy, ny);
+            float const bz0 = std::fmaf(n.n2[2], iz, nz), bz1 = std::fmaf(n.n2[3], iz, nz);
             float const amin = std::fmax(std::fmax(std::fmin(ax0, ax1), std::fmin(ay0, ay1)), std::fmax(std::fmin(az0, az1), 0.0f));
             float const amax = std::fmin(std::fmin(std::fmax(ax0, ax1), std::fmax(ay0, ay1)), std::fmin(std::fmax(az0, az1), tbest));
             float const bmin = std::fmax(std::fmax(std::fmin(bx0, bx1), std::fmin(by0, by1)), std::fmax(std::fmin(bz0, bz1), 0.0f));
