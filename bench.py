@@ -389,7 +389,7 @@ def main():
         }
         if scene == "spheres10k":
             # flop_per_path is the REFERENCE's algorithm (a 10 001-sphere linear scan per ray);
-            # the kernel answers the same queries through a bounding-volume hierarchy (~9 box pairs + ~2.4 sphere tests
+            # the kernel answers the same queries through a bounding-volume hierarchy (~10 box pairs + ~0.6 sphere tests
             # per ray), so "achieved" is an equivalent-work rate and may exceed the hardware peak -- not a pipe fraction
             line["roofline"]["frac"] = None
             line["roofline"]["equivalent_scan_frac"] = achieved / peak_tflops

@@ -19,6 +19,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
@@ -46,7 +47,8 @@ struct BvhTree
 
 namespace bvh_detail {
 
-constexpr int kLeafMax = 4;  // split until a node holds at most this many spheres ...
+constexpr int kLeafMax = 1;  // split until a node holds at most this many spheres (measured on config 5: 1 -> 112.9 ms, 2 -> 114.0,
+                             // 4 -> 117.1, 8 -> 117.0: leaf tests run at ~6 of 32 lanes, box tests at ~21) ...
 constexpr int kLeafHard = 8; // ... unless no split separates them (coincident centres): then up to this many per leaf
 constexpr int kBins = 16;
 
@@ -89,6 +91,7 @@ struct Builder
     std::vector<Box> boxes;
     std::vector<int> idx; // permutation being partitioned
     BvhTree tree;
+    int leaf_max = kLeafMax;
 
     explicit Builder(std::vector<BvhSphere> const& s) : sph(s)
     {
@@ -125,7 +128,7 @@ struct Builder
     {
         tree.max_depth = std::max(tree.max_depth, depth);
         int const n = e - b;
-        if(n <= kLeafMax) {
+        if(n <= leaf_max) {
             return make_leaf(b, e);
         }
         // binned SAH over the centroids
@@ -236,6 +239,10 @@ struct Builder
 inline BvhTree build_bvh(std::vector<BvhSphere> const& spheres)
 {
     bvh_detail::Builder b(spheres);
+    if(char const* e = std::getenv("PTB_BVH_LEAF")) { // experiments (dev/): spheres per leaf, 1..8
+        int const v = std::atoi(e);
+        b.leaf_max = v >= 1 && v <= bvh_detail::kLeafHard ? v : b.leaf_max;
+    }
     if(spheres.empty()) {
         b.tree.root = ~0; // empty leaf code is never traversed: callers test the sphere count first
         return std::move(b.tree);
