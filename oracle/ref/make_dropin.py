@@ -46,9 +46,46 @@ def patch(text: str) -> str:
     return text
 
 
+SANDBOX_BLOCK = '''    Vec* c = new Vec[w * h];
+    static_assert(sizeof(Sphere) == PTB_SPHERE_BYTES && sizeof(Vec) == 3 * sizeof(double), "the program's own records cross the boundary");
+    double const cam8[8] = { cam.o.x, cam.o.y, cam.o.z, cam.d.x, cam.d.y, cam.d.z, .5135, 140 };
+    ptb_context* gpu = nullptr;
+    if(ptb_create(/*device*/ 0, &gpu) != PTB_OK) {
+        fprintf(stderr, "%s\\n", ptb_last_error(nullptr));
+        return 1;
+    }
+    int rc = ptb_upload_scene(gpu, spheres, sizeof(spheres) / sizeof(Sphere), sizeof(Sphere));
+    rc = rc == PTB_OK ? ptb_set_smallpt_camera(gpu, cam8) : rc;
+    rc = rc == PTB_OK ? ptb_set_image(gpu, w, h, 2) : rc;
+    rc = rc == PTB_OK ? ptb_render(gpu, /*seed*/ 1, 0, static_cast<unsigned>(samps), PTB_INTEGRATOR_SMALLPT | PTB_PRECISION_FP32) : rc;
+    rc = rc == PTB_OK ? ptb_resolve(gpu, reinterpret_cast<double*>(c)) : rc;
+    if(rc != PTB_OK) {
+        fprintf(stderr, "%s\\n", ptb_last_error(gpu));
+        return 1;
+    }
+    ptb_destroy(gpu);
+
+'''
+
+
+def patch_sandbox(text: str) -> str:
+    """sandbox/main.cpp (the stand-alone smallpt fork): its OpenMP row loop (:236-269) becomes the ABI calls of
+    INTEGRATION.md section 2; scene array, camera constants and the PPM writer stay."""
+    if "#pragma omp parallel for" not in text:
+        raise SystemExit("make_dropin: the OpenMP loop of sandbox/main.cpp was not found -- has the reference changed?")
+    block = re.compile(r"^    Vec const cx = .*?(?=^    FILE\* f = fopen)", re.S | re.M)
+    text, n = block.subn(lambda _m: SANDBOX_BLOCK, text)
+    if n != 1:
+        raise SystemExit("make_dropin: the render loop of sandbox/main.cpp was not found exactly once")
+    if "erand48(Xi)" in text.split("int main")[1]:
+        raise SystemExit("make_dropin: the render loop is still there after the patch")
+    return "#include <ptb200.h> // C ABI of the B200 render loop\n" + text
+
+
 if __name__ == "__main__":
     src, dst = sys.argv[1], sys.argv[2]
     with open(src) as f:
-        out = patch(f.read())
+        body = f.read()
+    out = patch_sandbox(body) if "--sandbox" in sys.argv[3:] else patch(body)
     with open(dst, "w") as f:
         f.write(out)

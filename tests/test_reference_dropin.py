@@ -11,6 +11,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "_ref", "cpu_path_tracer_b200")
+SB_EXE = os.path.join(ROOT, "oracle", "_ref", "smallpt_b200")  # sandbox/main.cpp with the INTEGRATION.md section 2 patch
+PTB_SMALLPT = os.path.join(ROOT, "cpu-path-tracing_b200", "ptb_smallpt")
 PTB_MAIN = os.path.join(ROOT, "cpu-path-tracing_b200", "ptb_main")
 
 needs_exe = pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/cpu_path_tracer_b200 not built (no /root/reference here)")
@@ -71,3 +73,32 @@ def test_reference_program_renders_through_the_library(tmp_path):
     assert np.abs(img_a - img_b).max() <= 1
     assert (img_a == img_b).mean() > 0.999
     assert img_a.mean() > 20  # and it is a picture, not a black frame
+
+
+needs_sb = pytest.mark.skipif(not os.path.exists(SB_EXE), reason="oracle/_ref/smallpt_b200 not built (no /root/reference here)")
+
+
+@needs_sb
+def test_sandbox_program_binds_only_the_abi():
+    und = subprocess.run(["nm", "-D", "--undefined-only", SB_EXE], capture_output=True, text=True, check=True).stdout
+    bound = sorted(l.split()[-1] for l in und.splitlines() if " ptb_" in l)
+    assert bound == ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_render", "ptb_resolve", "ptb_set_image",
+                     "ptb_set_smallpt_camera", "ptb_upload_scene"]
+    # the program's own radiance() is still compiled (dead code now, hence erand48), its thread pool is gone
+    assert "omp_" not in und and "GOMP" not in und
+
+
+@needs_sb
+@pytest.mark.gpu
+def test_sandbox_program_renders_through_the_library(tmp_path):
+    """`smallpt_b200 64` (sandbox/main.cpp's CLI) against the library's own `ptb_smallpt 64`."""
+    a = subprocess.run([SB_EXE, "64"], cwd=tmp_path, capture_output=True, text=True)
+    assert a.returncode == 0, a.stderr
+    os.rename(tmp_path / "image.ppm", tmp_path / "ref_program.ppm")
+    b = subprocess.run([PTB_SMALLPT, "64"], cwd=tmp_path, capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    img_a, mx = read_ppm(tmp_path / "ref_program.ppm")
+    img_b, _ = read_ppm(tmp_path / "image.ppm")
+    assert mx == 255 and img_a.shape == (768, 1024, 3) == img_b.shape
+    assert np.abs(img_a - img_b).max() <= 1 and (img_a == img_b).mean() > 0.999
+    assert img_a.mean() > 20
