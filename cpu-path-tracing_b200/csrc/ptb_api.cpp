@@ -955,12 +955,14 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         SceneCounts const& c = ctx->counts;
         int const total = c.small_near + c.small_both + c.big_near + c.big_both;
         bool const unrollable = c.fits_const && total >= 1 && total <= (c.embed_ok ? 16 : 32);
-        if(variant == PTB_VARIANT_MEGAKERNEL_SORTED && precision == PTB_PRECISION_FP32 && codegen == PTB_CODEGEN_AUTO &&
-           ctx->n <= kSmemShadeSpheres && unrollable) {
+        if((variant == PTB_VARIANT_MEGAKERNEL_SORTED || variant == PTB_VARIANT_MEGAKERNEL) && precision == PTB_PRECISION_FP32 &&
+           codegen == PTB_CODEGEN_AUTO && ctx->n <= kSmemShadeSpheres && unrollable) {
             // worth ~0.3 s of compiling at once if this call alone traces >= 2^28 paths (~30 ms of rendering); a smaller
             // job compiles when the same scene is rendered a second time
             bool const eager = static_cast<uint64_t>(ctx->nslots) * samples_per_subpixel >= (1ull << 28);
-            jit_kernel = ctx->jit.get(ctx->cs, ctx->counts, sorted_inline, eager);
+            JitCache::Kind const kind = variant == PTB_VARIANT_MEGAKERNEL_SORTED ? JitCache::kSorted
+                                        : (smallpt ? JitCache::kInPlaceSmallpt : JitCache::kInPlacePt);
+            jit_kernel = ctx->jit.get(ctx->cs, ctx->counts, kind, sorted_inline, eager);
         }
     }
 
@@ -1040,7 +1042,13 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
             }
         }
         else {
-            PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches, smallpt));
+            ctx->last_launch_jit = jit_kernel != nullptr;
+            if(jit_kernel != nullptr) {
+                PTB_CUDA(ctx, ctx->jit.launch(*jit_kernel, p, ctx->cs, ctx->sm_count, st, &launches));
+            }
+            else {
+                PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches, smallpt));
+            }
         }
     }
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));

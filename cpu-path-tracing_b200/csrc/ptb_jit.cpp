@@ -109,16 +109,22 @@ int big_count(SceneCounts const& c)
 
 } // namespace
 
-std::string JitCache::kernel_name(SceneCounts const& c, int inline_material)
+std::string JitCache::kernel_name(SceneCounts const& c, Kind kind, int inline_material)
 {
-    char buf[256];
-    std::snprintf(buf, sizeof(buf), "ptb::mega_sorted_kernel<ptb::SceneShape<%d, %d, %d, %d, %d, %d, %d, %s, %s, %d>, true, %d>", c.small_near,
-                  c.small_both, c.big_near, c.big_both, c.big_x, c.big_y, c.big_z, c.uniform_k ? "true" : "false",
-                  c.embed_ok ? "true" : "false", c.pair_mask, inline_material == 0 ? 0 : 1);
+    char shape[160];
+    std::snprintf(shape, sizeof(shape), "ptb::SceneShape<%d, %d, %d, %d, %d, %d, %d, %s, %s, %d>", c.small_near, c.small_both, c.big_near,
+                  c.big_both, c.big_x, c.big_y, c.big_z, c.uniform_k ? "true" : "false", c.embed_ok ? "true" : "false", c.pair_mask);
+    char buf[320];
+    if(kind == kSorted) {
+        std::snprintf(buf, sizeof(buf), "ptb::mega_sorted_kernel<%s, true, %d>", shape, inline_material == 0 ? 0 : 1);
+    }
+    else {
+        std::snprintf(buf, sizeof(buf), "ptb::mega_kernel<%s, true, ptb::%s>", shape, kind == kInPlacePt ? "IntegratorPt" : "IntegratorSmallpt");
+    }
     return buf;
 }
 
-std::string JitCache::translation_unit(ConstSceneF32 const& cs, SceneCounts const& c)
+std::string JitCache::translation_unit(ConstSceneF32 const& cs, SceneCounts const& c, Kind kind)
 {
     int const ns = small_count(c), nb = big_count(c);
     std::string init = "{ { ";
@@ -152,11 +158,11 @@ std::string JitCache::translation_unit(ConstSceneF32 const& cs, SceneCounts cons
     init += "}, 0, 0, 0, 0 }";
 
     std::string tu;
-    tu += "// generated by ptb_jit.cpp: the sorted megakernel with this scene's coefficients as literals\n";
+    tu += "// generated by ptb_jit.cpp: a megakernel with this scene's coefficients as literals\n";
     tu += "#define PTB_JIT_SCENE_INIT " + init + "\n";
     tu += "#include \"ptb_kernels.h\"\n#include \"ptb_path_f32.cuh\"\n";
     tu += "namespace ptb { __constant__ ConstSceneF32 c_scene; }\n";
-    tu += "#include \"ptb_mega_sorted.cuh\"\n";
+    tu += kind == kSorted ? "#include \"ptb_mega_sorted.cuh\"\n" : "#include \"ptb_mega_inplace.cuh\"\n";
     return tu;
 }
 
@@ -171,7 +177,7 @@ bool JitCache::available()
     return state_ > 0;
 }
 
-JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, int inline_material, bool eager)
+JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Kind kind, int inline_material, bool eager)
 {
     if(!available() || !c.fits_const) {
         return nullptr;
@@ -183,7 +189,8 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, in
                                   static_cast<uint32_t>(c.big_x),      static_cast<uint32_t>(c.big_y),
                                   static_cast<uint32_t>(c.big_z),      static_cast<uint32_t>(c.uniform_k),
                                   static_cast<uint32_t>(c.embed_ok),   static_cast<uint32_t>(c.pair_mask),
-                                  static_cast<uint32_t>(inline_material == 0 ? 0 : 1) };
+                                  static_cast<uint32_t>(kind == kSorted ? (inline_material == 0 ? 0 : 1) : 0),
+                                  static_cast<uint32_t>(kind) };
     auto const push = [&](void const* p, size_t bytes) {
         size_t const n = bytes / sizeof(uint32_t);
         size_t const at = key.size();
@@ -226,8 +233,8 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, in
     Api& a = api();
     JitKernel k;
     auto const t0 = std::chrono::steady_clock::now();
-    std::string const tu = translation_unit(cs, c);
-    std::string const name = kernel_name(c, inline_material);
+    std::string const tu = translation_unit(cs, c, kind);
+    std::string const name = kernel_name(c, kind, inline_material);
     nvrtcProgram prog = nullptr;
     auto const fail = [&](std::string const& what) -> JitKernel const* {
         error_ = what;

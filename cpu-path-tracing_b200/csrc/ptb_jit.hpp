@@ -47,7 +47,10 @@ public:
     // otherwise a scene is compiled the SECOND time it is asked for -- geometry that changes every frame never is.
     // At most kMaxModules stay loaded (least recently used goes first).
     static constexpr size_t kMaxModules = 32;
-    JitKernel const* get(ConstSceneF32 const& cs, SceneCounts const& counts, int inline_material, bool eager);
+    // kind: which kernel -- the sorted megakernel scattering `inline_material` in place, or the in-place megakernel
+    // with the src/main.cpp or the sandbox integrator
+    enum Kind { kSorted = 0, kInPlacePt = 1, kInPlaceSmallpt = 2 };
+    JitKernel const* get(ConstSceneF32 const& cs, SceneCounts const& counts, Kind kind, int inline_material, bool eager);
     // Launch it: same grid policy and semantics as launch_megakernel_sorted.
     cudaError_t launch(JitKernel const& k, RenderParamsF32 const& p, ConstSceneF32 const& cs, int sm_count, cudaStream_t stream,
                        int* launches);
@@ -59,8 +62,8 @@ public:
     std::string const& last_error() const { return error_; }
 
     // The translation unit handed to NVRTC for a key (also what tests/ compile on the CPU to check the plumbing).
-    static std::string translation_unit(ConstSceneF32 const& cs, SceneCounts const& counts);
-    static std::string kernel_name(SceneCounts const& counts, int inline_material);
+    static std::string translation_unit(ConstSceneF32 const& cs, SceneCounts const& counts, Kind kind);
+    static std::string kernel_name(SceneCounts const& counts, Kind kind, int inline_material);
 
 private:
     std::map<std::vector<uint32_t>, JitKernel> cache_;

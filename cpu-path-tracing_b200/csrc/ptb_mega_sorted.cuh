@@ -107,14 +107,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
 #ifdef PTB_JIT_SCENE_INIT
     // Run-time compiled build (ptb_jit.cpp): the scene's coefficients arrive as LITERALS and fold into immediates of
     // the FFMA / FADD instructions -- no uniform loads in the scan, no register-file bandwidth for them either.
-    struct JitScene
-    {
-        SmallGeo small_geo[Shape::small_near + Shape::small_both > 0 ? Shape::small_near + Shape::small_both : 1];
-        BigGeo big_geo[Shape::big_near + Shape::big_both > 0 ? Shape::big_near + Shape::big_both : 1];
-        float axis_coef[Shape::big_near + Shape::big_both > 0 ? 2 * (Shape::big_near + Shape::big_both) : 2];
-        int n_small_near, n_small, n_big_near, n_big; // never read: specialised shapes carry their counts as types
-    };
-    JitScene const scene = PTB_JIT_SCENE_INIT;
+    JitSceneT<Shape> const scene = PTB_JIT_SCENE_INIT;
 #else
     ConstSceneF32 const& scene = c_scene;
 #endif

@@ -120,8 +120,10 @@ __device__ __forceinline__ void gen_primary(PathF32& p, CameraF32 const& cam, ui
     float const len = cam.sub_len;
     float const u0 = rng_uniform_f32(p.rng);
     float const u1 = rng_uniform_f32(p.rng);
-    float const xs = (static_cast<float>(x) + static_cast<float>(sx) * len) + len * u0;
-    float const ys = (static_cast<float>(y) + static_cast<float>(sy) * len) + len * u1;
+    // (explicit FMAs: where a * b + c * d leaves the choice of what to fuse to the compiler, two builds of this
+    //  header -- nvcc and the run-time compiler, or two kernels that inline it -- may round differently)
+    float const xs = fmaf(len, u0, fmaf(static_cast<float>(sx), len, static_cast<float>(x)));
+    float const ys = fmaf(len, u1, fmaf(static_cast<float>(sy), len, static_cast<float>(y)));
     float const s = xs * cam.inv_w;
     float const t = ys * cam.inv_h;
 
@@ -167,14 +169,17 @@ struct RayTerms
 __device__ __forceinline__ RayTerms ray_terms(PathF32 const& p, float k_uniform = 0.0f)
 {
     RayTerms r;
-    r.eps = kEpsilon * p.len;
+    // __fmul_rn: these products are ADDED to other terms in every sphere test; left as plain `*` the compiler may fuse
+    // them into those additions in one build and not in another (constant-bank vs immediate operands), which changes a
+    // last bit once in ~3e6 paths
+    r.eps = __fmul_rn(kEpsilon, p.len);
     r.od = fmaf(p.ox, p.dx, fmaf(p.oy, p.dy, p.oz * p.dz));
     r.oo = fmaf(p.ox, p.ox, fmaf(p.oy, p.oy, p.oz * p.oz));
     r.o2x = p.ox + p.ox;
     r.o2y = p.oy + p.oy;
     r.o2z = p.oz + p.oz;
-    r.kod = k_uniform * r.od;
-    r.koo = k_uniform * r.oo;
+    r.kod = __fmul_rn(k_uniform, r.od);
+    r.koo = __fmul_rn(k_uniform, r.oo);
     return r;
 }
 
@@ -417,6 +422,17 @@ using GenericShape = SceneShape<-1, -1, -1, -1>;
 // kKeepReg: the mantissa mask comes in a REGISTER (keep_reg, loaded once per kernel through an opaque move) so
 // that "(key & mask) | position" is a single three-input LOP3 with the position as its immediate; with both as
 // immediates the compiler needs two LOP3 per sphere.
+// What a run-time compiled kernel (ptb_jit.cpp) reads its sphere coefficients from: the same members closest_hit
+// takes from the constant bank, initialised from literals so that they fold into instruction immediates.
+template<class Shape>
+struct JitSceneT
+{
+    SmallGeo small_geo[Shape::small_near + Shape::small_both > 0 ? Shape::small_near + Shape::small_both : 1];
+    BigGeo big_geo[Shape::big_near + Shape::big_both > 0 ? Shape::big_near + Shape::big_both : 1];
+    float axis_coef[Shape::big_near + Shape::big_both > 0 ? 2 * (Shape::big_near + Shape::big_both) : 2];
+    int n_small_near, n_small, n_big_near, n_big; // never read: specialised shapes carry their counts as types
+};
+
 template<class Shape, bool kKeepReg = false, class Scene = ConstSceneF32>
 __device__ __forceinline__ bool closest_hit(Scene const& cs, GeoLists const& gl, PathF32 const& p,
                                             RayTerms const& r, float& t_out, int& id_out, uint32_t keep_reg = 0u)
@@ -636,22 +652,26 @@ __device__ __forceinline__ void scatter_diffuse(PathF32& p, float fx, float fy, 
     float const sin_t = fast_sqrt(u2);
     float const cos_t = fast_sqrt(1.0f - u2);
     // u = norm((|w.x| > 0.1 ? (0,1,0) : (1,0,0)) x w), v = w x u
-    float ux, uy, uz;
+    // v = w x u written out per branch, the two-term components with the fused operand pinned (see gen_primary)
+    float ux, uy, uz, vx, vy, vz;
     if(fabsf(fx) > 0.1f) {
-        float const inv = fast_rsqrt(fmaf(fz, fz, fx * fx));
+        float const inv = fast_rsqrt(fmaf(fz, fz, __fmul_rn(fx, fx)));
         ux = fz * inv;
         uy = 0.0f;
         uz = -fx * inv;
+        vx = fy * uz;
+        vy = fmaf(fz, ux, -__fmul_rn(fx, uz));
+        vz = -(fy * ux);
     }
     else {
-        float const inv = fast_rsqrt(fmaf(fz, fz, fy * fy));
+        float const inv = fast_rsqrt(fmaf(fz, fz, __fmul_rn(fy, fy)));
         ux = 0.0f;
         uy = -fz * inv;
         uz = fy * inv;
+        vx = fmaf(fy, uz, -__fmul_rn(fz, uy));
+        vy = -(fx * uz);
+        vz = fx * uy;
     }
-    float const vx = fy * uz - fz * uy;
-    float const vy = fz * ux - fx * uz;
-    float const vz = fx * uy - fy * ux;
     float const cu = cphi * sin_t, cv = sphi * sin_t;
     p.dx = fmaf(ux, cu, fmaf(vx, cv, fx * cos_t));
     p.dy = fmaf(uy, cu, fmaf(vy, cv, fy * cos_t));

@@ -75,7 +75,7 @@ enum
     PTB_ACCEL_AUTO = 0x0000, /* bounding-volume hierarchy built at upload: same hits, O(log n) per ray */
     PTB_ACCEL_SCAN = 0x1000, /* the reference's linear scan over every sphere (src/main.cpp:30-42) */
     PTB_ACCEL_MASK = 0xF000,
-    /* code generation of the sorted megakernel for scenes with a specialised layout (<= 16 spheres) */
+    /* code generation of the FP32 megakernels (sorted and in-place) for scenes of up to 16 spheres */
     PTB_CODEGEN_AUTO = 0x00000,        /* compile the kernel for THIS scene at run time (NVRTC, sphere coefficients as
                                           immediates; cached per scene) when libnvrtc is present, else precompiled */
     PTB_CODEGEN_PRECOMPILED = 0x10000, /* always the precompiled kernel (coefficients from the constant bank) */
@@ -177,7 +177,7 @@ int ptb_get_stats(ptb_context* ctx, ptb_stats* out);
  * a fully unrolled kernel exists for this layout (0/1). */
 int ptb_scene_layout(ptb_context* ctx, int32_t out[10]);
 /* Run-time code generation (PTB_CODEGEN_AUTO): out = { available (libnvrtc + libcuda found, PTB_JIT != 0), kernels
- * compiled so far, failed attempts, 1 if the last FP32 sorted-megakernel launch ran a run-time compiled kernel,
+ * compiled so far, failed attempts, 1 if the last FP32 megakernel launch ran a run-time compiled kernel,
  * total compile time in ms }.  A failed attempt is not an error of ptb_render: the precompiled kernel runs instead;
  * ptb_jit_last_error says what happened (empty string when nothing did). */
 int ptb_jit_info(ptb_context* ctx, int32_t out[5]);

@@ -432,6 +432,40 @@ def test_runtime_compilation_of_a_one_sphere_scene(gpu, oracle_port, refl):
         assert np.abs(r.resolve() - ref).mean() < 2e-3
 
 
+def test_runtime_compiled_in_place_megakernels(gpu):
+    """The in-place megakernel is compiled for the scene too -- with the src/main.cpp integrator and with the sandbox
+    one: same slots, same counters as the precompiled kernels."""
+    W, H, S = 160, 90, 8
+    sph, cfg = gpu.builtin_scene("box_mirror", W, H)
+    cam = gpu.camera_with_config(cfg)
+    sb_sph, sb_cam = gpu.builtin_smallpt_scene()
+    cases = [(sph, cam, None, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL),
+             (sb_sph, None, sb_cam, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL | gpu.INTEGRATOR_SMALLPT)]
+    for spheres, camera, sbcam, flags in cases:
+        with gpu.Renderer(0) as r:
+            r.upload_scene(spheres)
+            if camera is not None:
+                r.set_camera(camera)
+            if sbcam is not None:
+                r.set_smallpt_camera(sbcam)
+            r.set_image(W, H, 2)
+            if not r.jit_info()["available"]:
+                pytest.skip("run-time compilation not available")
+            r.render(3, 0, S, flags | gpu.CODEGEN_PRECOMPILED)
+            pre, st_p = r.download_accum(), r.stats()
+            r.clear()
+            r.render(3, 0, S, flags)
+            r.clear()
+            r.render(3, 0, S, flags)
+            info = r.jit_info()
+            assert info["failures"] == 0 and info["last_launch_jit"] == 1, info["last_error"]
+            jit, st_j = r.download_accum(), r.stats()
+        assert np.all(pre[:, 3] == S) and np.all(jit[:, 3] == S)
+        assert (st_j.rays, st_j.hits_diffuse, st_j.hits_specular, st_j.hits_dielectric) == \
+            (st_p.rays, st_p.hits_diffuse, st_p.hits_specular, st_p.hits_dielectric)
+        assert np.isclose(pre[:, :3], jit[:, :3], rtol=1e-5, atol=1e-5).all()
+
+
 def test_runtime_compilation_follows_the_scene(gpu):
     """Different coefficients -> a different kernel; a scene without a specialised layout -> the precompiled path."""
     W, H = 64, 36
