@@ -957,9 +957,10 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         bool const unrollable = c.fits_const && total >= 1 && total <= (c.embed_ok ? 16 : 32);
         if((variant == PTB_VARIANT_MEGAKERNEL_SORTED || variant == PTB_VARIANT_MEGAKERNEL) && precision == PTB_PRECISION_FP32 &&
            codegen == PTB_CODEGEN_AUTO && ctx->n <= kSmemShadeSpheres && unrollable) {
-            // worth ~0.3 s of compiling at once if this call alone traces >= 2^28 paths (~30 ms of rendering); a smaller
-            // job compiles when the same scene is rendered a second time
-            bool const eager = static_cast<uint64_t>(ctx->nslots) * samples_per_subpixel >= (1ull << 28);
+            // Compiling costs 0.2-0.3 s and buys ~5 %: it pays for itself after ~5 s of rendering.  A single call that large
+            // (>= 2^35 paths) compiles at once; otherwise the kernel is compiled when the same scene is rendered a second
+            // time (progressive rendering, benchmarks, animations with a static scene).
+            bool const eager = static_cast<uint64_t>(ctx->nslots) * samples_per_subpixel >= (1ull << 35);
             JitCache::Kind const kind = variant == PTB_VARIANT_MEGAKERNEL_SORTED ? JitCache::kSorted
                                         : (smallpt ? JitCache::kInPlaceSmallpt : JitCache::kInPlacePt);
             jit_kernel = ctx->jit.get(ctx->cs, ctx->counts, kind, sorted_inline, eager);

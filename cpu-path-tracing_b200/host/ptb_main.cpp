@@ -8,6 +8,7 @@
 //
 //   ptb_main [spp] [--scene simple|box|box_mirror|dof_glass|spheres10k] [--size WxH]
 //            [--seed N] [--fp64] [--out image.ppm] [--device N]
+//            [--variant sorted|inplace|wavefront] [--precompiled] [--scan]
 #include "../../include/ptb200.h"
 #include "pt.hpp"
 
@@ -66,6 +67,21 @@ auto main(int argc, char* argv[]) -> int
         }
         else if(a == "--fp64") {
             flags = PTB_VARIANT_MEGAKERNEL | PTB_PRECISION_FP64;
+        }
+        else if(a == "--variant") {
+            std::string const v = next();
+            unsigned const var = v == "sorted" ? PTB_VARIANT_MEGAKERNEL_SORTED : (v == "inplace" ? PTB_VARIANT_MEGAKERNEL : (v == "wavefront" ? PTB_VARIANT_WAVEFRONT : 0xFu));
+            if(var == 0xFu) {
+                std::cerr << "--variant wants sorted, inplace or wavefront\n";
+                return 2;
+            }
+            flags = (flags & ~static_cast<unsigned>(PTB_VARIANT_MASK)) | var;
+        }
+        else if(a == "--precompiled") { // no run-time compilation for the scene
+            flags |= PTB_CODEGEN_PRECOMPILED;
+        }
+        else if(a == "--scan") { // the reference's linear closest-hit scan even when a hierarchy exists
+            flags |= PTB_ACCEL_SCAN;
         }
         else {
             spp = std::stoi(a); // throws on garbage, like the reference's std::stoi (main.cpp:206)
@@ -127,7 +143,10 @@ auto main(int argc, char* argv[]) -> int
     ptb_stats st{};
     ptb_get_stats(ctx, &st);
     double const wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-    std::cerr << "  device " << st.last_render_ms << " ms, wall " << wall_ms << " ms, "
+    int32_t jit[5] = { 0, 0, 0, 0, 0 };
+    ptb_jit_info(ctx, jit);
+    std::cerr << "  " << (jit[3] != 0 ? "kernel compiled for this scene at run time, " : "precompiled kernel, ")
+              << "device " << st.last_render_ms << " ms, wall " << wall_ms << " ms, "
               << static_cast<double>(st.paths) / (st.last_render_ms > 0 ? st.last_render_ms : 1) * 1e-3 << " Mpaths/s, "
               << static_cast<double>(st.rays) / (st.last_render_ms > 0 ? st.last_render_ms : 1) * 1e-3 << " Mrays/s\n";
 
