@@ -945,7 +945,8 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     // Scene-specialised code: compiled (once per scene, ~0.4 s) BEFORE the timed region starts.
     int sorted_inline = ctx->inline_material;
     if(char const* force = std::getenv("PTB_INLINE_MATERIAL")) { // experiments (dev/)
-        sorted_inline = std::atoi(force) == 0 ? 0 : 1;
+        int const f = std::atoi(force);
+        sorted_inline = f < 0 ? -1 : f == 0 ? 0 : 1;
     }
     JitKernel const* jit_kernel = nullptr;
     // Any layout that fits the unrolled scan qualifies, not only the ones the library ships precompiled: a scene of up to

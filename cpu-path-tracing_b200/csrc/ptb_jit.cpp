@@ -116,7 +116,7 @@ std::string JitCache::kernel_name(SceneCounts const& c, Kind kind, int inline_ma
                   c.big_both, c.big_x, c.big_y, c.big_z, c.uniform_k ? "true" : "false", c.embed_ok ? "true" : "false", c.pair_mask);
     char buf[320];
     if(kind == kSorted) {
-        std::snprintf(buf, sizeof(buf), "ptb::mega_sorted_kernel<%s, true, %d>", shape, inline_material == 0 ? 0 : 1);
+        std::snprintf(buf, sizeof(buf), "ptb::mega_sorted_kernel<%s, true, %d>", shape, inline_material < 0 ? -1 : inline_material == 0 ? 0 : 1);
     }
     else {
         std::snprintf(buf, sizeof(buf), "ptb::mega_kernel<%s, true, ptb::%s>", shape, kind == kInPlacePt ? "IntegratorPt" : "IntegratorSmallpt");
@@ -189,7 +189,7 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
                                   static_cast<uint32_t>(c.big_x),      static_cast<uint32_t>(c.big_y),
                                   static_cast<uint32_t>(c.big_z),      static_cast<uint32_t>(c.uniform_k),
                                   static_cast<uint32_t>(c.embed_ok),   static_cast<uint32_t>(c.pair_mask),
-                                  static_cast<uint32_t>(kind == kSorted ? (inline_material == 0 ? 0 : 1) : 0),
+                                  static_cast<uint32_t>(kind == kSorted ? (inline_material < 0 ? 2 : inline_material == 0 ? 0 : 1) : 0),
                                   static_cast<uint32_t>(kind) };
     auto const push = [&](void const* p, size_t bytes) {
         size_t const n = bytes / sizeof(uint32_t);

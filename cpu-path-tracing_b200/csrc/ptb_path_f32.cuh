@@ -40,12 +40,37 @@ __device__ __forceinline__ float fast_sqrt(float x)
     return r;
 }
 // sqrt of the sphere discriminant: MUFU.SQRT; x < 0 -> NaN, which the key ordering treats
-// as a miss.  (x * rsqrt(x) halves the XU-pipe time, MUFU.RSQ being twice as fast as
-// MUFU.SQRT on B200, but rendered wrong images in a first attempt -- see DESIGN.md,
-// "tried and dropped"; the XU pipe is not the limiter anyway.)
+// as a miss.
 __device__ __forceinline__ float disc_sqrt(float x)
 {
     return fast_sqrt(x);
+}
+// a + sqrt(x) and a - sqrt(x) for a discriminant x.  PTB_DISC_RSQRT (an experiment, off): sqrt(x) = x * rsqrt(x) folded
+// into the addition -- MUFU.RSQ + FFMA instead of MUFU.SQRT + FADD, same instruction count, half the XU-pipe time; x = 0
+// gives NaN = miss where sqrt gives a grazing hit.  Measured 0.4 % (box_mirror) and 0.75 % (box) SLOWER than MUFU.SQRT:
+// the XU pipe is not what limits the scan ("tried and dropped").
+__device__ __forceinline__ float add_root(float a, float x)
+{
+#ifdef PTB_DISC_RSQRT
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return fmaf(x, y, a);
+#else
+    return a + disc_sqrt(x);
+#endif
+}
+__device__ __forceinline__ void sub_add_root(float a, float x, float& lo, float& hi)
+{
+#ifdef PTB_DISC_RSQRT
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    lo = fmaf(-x, y, a);
+    hi = fmaf(x, y, a);
+#else
+    float const sq = disc_sqrt(x);
+    lo = a - sq;
+    hi = a + sq;
+#endif
 }
 __device__ __forceinline__ float fast_rcp(float x)
 {
@@ -217,12 +242,11 @@ __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& 
         float const cc = fmaf(cx, cx, fmaf(cy, cy, fmaf(cz, cz, -s.r2))); // c (sphere.cpp:11)
         disc = fmaf(nb, nb, -cc);
     }
-    float const sq = disc_sqrt(disc);
     float const h = nb - r.eps;
-    float const tn = h - sq;
+    float tn, tf;
+    sub_add_root(h, disc, tn, tf);
     uint32_t key;
     if constexpr(kBoth) {
-        float const tf = h + sq;
         key = min(__float_as_uint(tn), __float_as_uint(tf));
     }
     else {
@@ -245,7 +269,7 @@ __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, R
     float const hb = fmaf(p.dx, b.gx, fmaf(p.dy, b.gy, fmaf(p.dz, b.gz, b.k * r.od)));           // half_b / 2R
     float const cp = fmaf(r.o2x, b.gx, fmaf(r.o2y, b.gy, fmaf(r.o2z, b.gz, fmaf(b.k, r.oo, b.K)))); // c / 2R
     float const disc = fmaf(hb, hb, -(b.k * cp));
-    float const m = disc_sqrt(disc) + fabsf(hb);
+    float const m = add_root(fabsf(hb), disc);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u; // sign bit set when hb >= 0 (sigma = -1)
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
     float const t1 = fmaf(cs, fast_rcp(m), -r.eps);
@@ -278,7 +302,7 @@ __device__ __forceinline__ uint32_t key_big_axis(float ga, float K, float k, Pat
     float const hb = fmaf(da, ga, kUniformK ? r.kod : k * r.od);
     float const cp = fmaf(oa2, ga, kUniformK ? r.koo + K : fmaf(k, r.oo, K));
     float const disc = fmaf(hb, hb, -(k * cp));
-    float const m = disc_sqrt(disc) + fabsf(hb);
+    float const m = add_root(fabsf(hb), disc);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
     return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
@@ -301,7 +325,7 @@ __device__ __forceinline__ uint32_t key_big_pair(float ga, float K, float k, Pat
     float const hb = fmaf(-fabsf(da), G, r.kod);
     float const cp = fmaf(-__uint_as_float(__float_as_uint(oa2) ^ sign), G, r.koo + K);
     float const disc = fmaf(hb, hb, -(k * cp));
-    float const m = disc_sqrt(disc) + fabsf(hb);
+    float const m = add_root(fabsf(hb), disc);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
     float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
     sel = sign >> 31;
@@ -365,10 +389,11 @@ __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 cons
                 int const pos = pw & 0x7fffffff;
                 float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz;
                 float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));
-                float const sq = disc_sqrt(small_disc_far(cx, cy, cz, nb, s.r2, p));
                 float const h = nb - r.eps;
-                uint32_t const kn = __float_as_uint(h - sq);
-                uint32_t key = pw < 0 ? min(kn, __float_as_uint(h + sq)) : kn; // key_small<kBoth>
+                float tn, tf;
+                sub_add_root(h, small_disc_far(cx, cy, cz, nb, s.r2, p), tn, tf);
+                uint32_t const kn = __float_as_uint(tn);
+                uint32_t key = pw < 0 ? min(kn, __float_as_uint(tf)) : kn; // key_small<kBoth>
                 key = p.last == pos ? __float_as_uint(nb + h) : key;           // key_small<., kRobust>: standing on it
                 if(key < best || (key == best && pos < id)) {
                     best = key;
