@@ -648,6 +648,52 @@ def test_generic_kernel_for_unspecialised_scene(gpu, oracle_port):
     assert np.abs(img - ref).mean() < 1e-2
 
 
+@pytest.mark.parametrize("n", [16, 17, 64, 65, 400])
+def test_random_scenes_on_both_sides_of_every_size_threshold(gpu, oracle_port, n):
+    """Random overlapping spheres of every material around the library's size thresholds: <= 16 small spheres can be
+    unrolled (run-time build), <= 64 take the run-time-count scan over constant memory, more go through the hierarchy.
+    Each path must give the FP64 oracle's primary hits, an unbiased image, and -- scan against hierarchy -- the very
+    same bounces."""
+    rng = np.random.default_rng(100 + n)
+    s = np.zeros(n, dtype=gpu.SPHERE_DTYPE)
+    s["radius"] = rng.uniform(0.03, 0.25, n) * (1.0 if n <= 65 else 0.4)
+    s["position"] = rng.uniform(-1.2, 1.2, (n, 3)) * (1, 0.6, 1) + (0, 0.1, -1.2)
+    s["color"] = rng.uniform(0.2, 0.95, (n, 3))
+    s["emission"][::7] = (3, 2.5, 2)
+    s["reflection"] = rng.integers(0, 3, n)
+    s[0] = (1000.0, (0, -1000.6, -1), (0, 0, 0), (0.5, 0.5, 0.5), 0, 0)  # the ground: a big sphere
+    W, H, S = 96, 64, 4
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    ref = oracle_port.render(s, cam, W, H, S, 2, 21, 0)
+    xs, ys, sx, sy, ss = probe_inputs(rng, W, H, 20000)
+    ohit, orad, _, _ = oracle_port.samples(s, cam, W, H, 2, 21, xs, ys, sx, sy, ss)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, s, cam, W, H) as r:
+        hit_a, rad_a, ray_a, _ = r.trace_samples(21, xs, ys, sx, sy, ss, gpu.PRECISION_FP32 | gpu.ACCEL_AUTO)
+        hit_s, rad_s, ray_s, _ = r.trace_samples(21, xs, ys, sx, sy, ss, gpu.PRECISION_FP32 | gpu.ACCEL_SCAN)
+        r.render(21, 0, S, flags)
+        r.clear()
+        r.render(21, 0, S, flags)  # second sight: the run-time build where the layout allows one
+        acc, img, st_a = r.download_accum(), r.resolve(), r.stats()
+        r.clear()
+        r.render(21, 0, S, flags | gpu.ACCEL_SCAN | gpu.CODEGEN_PRECOMPILED)
+        img_scan, st_s = r.resolve(), r.stats()
+        r.clear()
+        r.render(21, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL)
+        img_inplace = r.resolve()
+    assert np.array_equal(hit_a, hit_s) and np.array_equal(rad_a, rad_s) and np.array_equal(ray_a, ray_s)
+    assert np.isfinite(rad_a).all() and np.isfinite(acc).all() and np.all(acc[:, 3] == S)
+    assert (hit_a == ohit).mean() >= 0.999
+    assert (rel_err(rad_a, orad) <= 1e-3).mean() >= 0.96
+    se = np.sqrt((rad_a.var(axis=0) + orad.var(axis=0)) / len(rad_a))
+    assert np.abs((rad_a.mean(axis=0) - orad.mean(axis=0)) / se).max() < 4.0
+    assert abs(st_a.rays - st_s.rays) <= 3e-3 * st_s.rays
+    for im in (img, img_scan, img_inplace):
+        assert np.abs(im - ref).mean() < 1e-2
+        assert abs(im.mean() - ref.mean()) < 5e-3
+
+
 def test_scene_layouts_take_the_specialised_kernels(gpu):
     expect = {
         "box": dict(small_near=2, small_both=1, big_near=5, big_both=0, big_x=2, big_y=2, big_z=1, uniform_k=1, specialised=1),
