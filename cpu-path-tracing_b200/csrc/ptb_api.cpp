@@ -14,8 +14,19 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
+
+// The precompiled FP32 kernels read the packed scene from ONE __constant__ symbol per device (ptb_f32.cu: c_scene), filled
+// stream-ordered at the start of every render.  Two contexts on the same GPU driven from two host threads would overwrite
+// it under each other's running kernel; rendering calls are blocking and each fills the whole GPU anyway, so they simply
+// take turns.
+static std::mutex& device_render_mutex(int device)
+{
+    static std::mutex m[64];
+    return m[static_cast<unsigned>(device) % 64u];
+}
 
 using namespace ptb;
 
@@ -932,6 +943,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         ctx->stats.last_render_ms = 0.0;
         return PTB_OK; // the reference renders a black image for spp < 4 (main.cpp:206)
     }
+    std::lock_guard<std::mutex> const turn(device_render_mutex(ctx->device));
     cudaStream_t st = ctx->stream;
     if(variant == PTB_VARIANT_WAVEFRONT && st == nullptr) {
         // CUDA graphs cannot be captured on the legacy default stream: drain it and use the private one;
@@ -1296,6 +1308,7 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
        radiance_out == nullptr || count > (1u << 30)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: null pointer");
     }
+    std::lock_guard<std::mutex> const turn(device_render_mutex(ctx->device));
     uint32_t const precision = flags & PTB_PRECISION_MASK;
     if(precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: unknown flags");

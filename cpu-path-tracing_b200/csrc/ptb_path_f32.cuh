@@ -383,15 +383,18 @@ __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 cons
         else {
             int const code = ~node;
             int const first = code >> 3, count = (code & 7) + 1;
+            // leaves hold ONE sphere (ptb_bvh.hpp; up to 8 only where coincident centres cannot be split): no unrolling,
+            // and the 16-byte record comes in one load
+#pragma unroll 1
             for(int k = 0; k < count; ++k) {
-                SmallGeo const s = gl.bvh_geo[first + k];
-                int const pw = gl.bvh_pos[first + k];
+                float4 const s = __ldg(reinterpret_cast<float4 const*>(gl.bvh_geo) + (first + k)); // cx, cy, cz, r^2
+                int const pw = __ldg(gl.bvh_pos + (first + k));
                 int const pos = pw & 0x7fffffff;
-                float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz;
+                float const cx = s.x - p.ox, cy = s.y - p.oy, cz = s.z - p.oz;
                 float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));
                 float const h = nb - r.eps;
                 float tn, tf;
-                sub_add_root(h, small_disc_far(cx, cy, cz, nb, s.r2, p), tn, tf);
+                sub_add_root(h, small_disc_far(cx, cy, cz, nb, s.w, p), tn, tf);
                 uint32_t const kn = __float_as_uint(tn);
                 uint32_t key = pw < 0 ? min(kn, __float_as_uint(tf)) : kn; // key_small<kBoth>
                 key = p.last == pos ? __float_as_uint(nb + h) : key;           // key_small<., kRobust>: standing on it

@@ -19,7 +19,8 @@
  * throws across the boundary; the caller owns every host buffer it passes; the
  * library owns all device memory behind the opaque context.  A context is bound
  * to ONE GPU and is not thread-safe (one process / one host thread per GPU, as
- * under torchrun).  There is NO CPU fallback: without a usable CUDA device
+ * under torchrun); several contexts may be driven from several threads, renders
+ * on the same GPU then take turns.  There is NO CPU fallback: without a usable CUDA device
  * ptb_create fails with PTB_ERR_NO_DEVICE.
  */
 #ifndef PTB200_H

@@ -716,6 +716,44 @@ def test_scene_layouts_take_the_specialised_kernels(gpu):
         assert r.scene_layout()["big_both"] == 1
 
 
+def test_two_contexts_on_one_gpu_from_two_threads(gpu):
+    """Contexts are single-threaded, but two of them may live in two host threads on the same GPU: the precompiled
+    kernels share one constant-memory scene per device, so concurrent renders must take turns and not mix scenes."""
+    import threading
+    W, H, S = 160, 90, 16
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED | gpu.CODEGEN_PRECOMPILED
+    jobs = []
+    for name in ("box", "box_mirror"):
+        sph, cfg = gpu.builtin_scene(name, W, H)
+        jobs.append((sph, gpu.camera_with_config(cfg)))
+    alone = []
+    for sph, cam in jobs:
+        with make_renderer(gpu, sph, cam, W, H) as r:
+            r.render(3, 0, S, flags)
+            alone.append((r.download_accum(), r.stats().rays))
+    together = [None, None]
+
+    def work(i):
+        sph, cam = jobs[i]
+        with make_renderer(gpu, sph, cam, W, H) as r:
+            rays = 0
+            for k in range(8):  # many short renders so that the two threads really interleave
+                r.render(3, 2 * k, 2, flags)
+            together[i] = (r.download_accum(), r.stats().rays)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for (acc_a, rays_a), got in zip(alone, together):
+        assert got is not None
+        acc_t, rays_t = got
+        assert rays_t == rays_a
+        assert np.all(acc_t[:, 3] == S)
+        assert np.isclose(acc_t[:, :3], acc_a[:, :3], rtol=1e-5, atol=1e-5).all()
+
+
 def test_error_behaviour(gpu):
     with gpu.Renderer(0) as r:
         with pytest.raises(gpu.PtbError) as e:
