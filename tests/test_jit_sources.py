@@ -41,7 +41,8 @@ def test_embedded_sources_are_the_sources(tmp_path):
     csrc = os.path.join(ROOT, "cpu-path-tracing_b200", "csrc")
     subprocess.run([sys.executable, os.path.join(csrc, "gen_jit_sources.py"), csrc, str(out)], check=True)
     text = out.read_text()
+    joined = text.replace(')PTBJIT"\n    R"PTBJIT(', "")  # long headers are split into chunks the compiler concatenates
     for h in ("ptb_types.h", "ptb_rng.cuh", "ptb_scene.cuh", "ptb_kernels.h", "ptb_path_f32.cuh", "ptb_mega_sorted.cuh"):
         assert '"%s"' % h in text
         body = open(os.path.join(csrc, h)).read()
-        assert body[:200] in text and body[-200:] in text
+        assert body in joined
