@@ -334,9 +334,24 @@ PackedScene pack_geometry(ptb_context* ctx)
     if(ctx->have_sbcam) {
         extent = std::max(extent, reach(ctx->sb_cam8));
     }
-    out.counts.embed_ok = extent <= 8.0;
+    // A ray INSIDE a huge sphere (camera inside it, or a huge glass ball) can travel its whole diameter: the paths are then
+    // not confined to `extent` at all, and the plain root formulas lose the next hit of a ray that starts on that sphere
+    // (found by dev/fuzz_scenes.py: 1.5 % of the rays inside a R = 1000 ground escaped to the sky).  Such scenes take the
+    // full-precision keys and the exact self-sphere roots, like the sandbox scene does.
+    // The same goes, on a smaller scale, for an ordinary sphere that rays travel INSIDE of (glass, or the camera sits in
+    // it): a ray that starts on it sees its own surface at c / 2 half_b with c = r^2 * 1e-7 of rounding noise, which passes
+    // epsilon = 1e-4 for grazing rays once r is a few units -- and inside a mirror ball a grazing ray stays grazing (a
+    // camera in a r = 5 mirror ball traced 22 % more rays than the oracle's arithmetic).  The reference's glass balls have
+    // r <= 0.5; one unit is the limit for the plain formulas.
+    double max_inside_radius = 0.0;
+    for(int i : lists[1]) {
+        max_inside_radius = std::max(max_inside_radius, s[i].radius);
+    }
+    out.counts.embed_ok = extent <= 8.0 && out.counts.big_both == 0 && max_inside_radius <= 1.0;
     if(!out.counts.embed_ok) {
-        out.counts.pair_mask = 0; // the paired test exists for the index-in-key kernels only
+        // the paired and the axis tests exist for the index-in-key kernels only: they have no exact self-sphere root
+        out.counts.pair_mask = 0;
+        out.counts.big_x = out.counts.big_y = out.counts.big_z = 0;
     }
     out.counts.fits_const = out.counts.small_near + out.counts.small_both <= kMaxConstSpheres &&
                             out.counts.big_near + out.counts.big_both <= kMaxConstSpheres;

@@ -51,7 +51,7 @@ namespace ptb {
     X(3, 1, 1, 0, 0, 1, 0, true, true, 0)   /* simple_scene.hpp: mirror, centre, light | glass | ground (R=100, on the y axis)                       */ \
     X(2, 2, 1, 0, 0, 1, 0, true, true, 0)   /* depth-of-field scene (BASELINE config 4): two glass spheres                                             */ \
     X(2, 1, 5, 0, 0, 0, 0, false, true, 0)  /* box scenes in a frame where the walls are not axis spheres                                             */ \
-    X(0, 3, 0, 5, 0, 0, 0, false, true, 0)  /* box scenes with the camera inside every sphere's reach: all both-roots                                 */ \
+    X(0, 3, 0, 5, 0, 0, 0, false, false, 0) /* box scenes with the camera inside every sphere's reach: all both-roots (full-precision keys)           */ \
     X(3, 1, 0, 6, 0, 0, 0, true, false, 0)  /* sandbox/main.cpp: 2 mirrors + light | glass | six R=1e5 walls seen from INSIDE; ~300 units across     */ \
     X(1, 0, 0, 0, 0, 0, 0, false, true, 0) \
     X(0, 1, 0, 0, 0, 0, 0, false, true, 0) \

@@ -409,6 +409,56 @@ def test_runtime_compilation_specialises_layouts_the_library_does_not_ship(gpu, 
     assert (np.abs(img_jit - ref) < 1e-4).mean() > 0.8
 
 
+def _inside_scenes(gpu):
+    """Scenes whose rays travel INSIDE a sphere that is large against epsilon (found by dev/fuzz_scenes.py): the plain
+    root formulas of the index-in-key kernels are not good enough there, the layout must say so (embed_ok = 0)."""
+    W, H = 64, 48
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    ground = (1000.0, (0, -1000.5, -1.5), (0, 0, 0), (0.5, 0.5, 0.5), 0, 0)
+    lamp = (0.2, (0.3, 0.0, -1.0), (4, 4, 4), (0.7, 0.7, 0.7), 0, 0)
+    glass = (0.25, (-0.4, -0.2, -1.2), (0, 0, 0), (0.9, 0.9, 0.9), 2, 0)
+    out = []
+    # the camera 2 cm below the surface of the R = 1000 ground
+    c = cfg.copy()
+    c["position"][0], c["direction"][0], c["aperture"][0] = (0.0, -0.52, 0.5), (0.0, -0.6, -1.0), 0.0
+    out.append(("camera inside the ground", [ground, lamp, glass], c))
+    # the camera inside a r = 5 mirror ball that also holds a lamp: grazing rays stay grazing
+    c = cfg.copy()
+    c["position"][0], c["direction"][0], c["aperture"][0] = (0.5, 0.2, -1.0), (0.0, 0.0, -3.0), 0.0
+    out.append(("camera inside a mirror ball", [(5.0, (0, 0, -1.5), (0, 0, 0), (0.9, 0.9, 0.9), 1, 0), lamp, glass], c))
+    # a big glass ball seen from outside
+    c = cfg.copy()
+    out.append(("glass ball of radius 3", [(3.0, (0, 0, -5.0), (0, 0, 0), (0.95, 0.95, 0.95), 2, 0), lamp,
+                                             (100.0, (0, -103.5, -5.0), (0, 0, 0), (0.5, 0.5, 0.5), 0, 0)], c))
+    return W, H, out
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_rays_inside_large_spheres_take_the_exact_self_roots(gpu, oracle_port, which):
+    W, H, scenes = _inside_scenes(gpu)
+    label, rows, cfg = scenes[which]
+    s = np.zeros(len(rows), dtype=gpu.SPHERE_DTYPE)
+    for i, row in enumerate(rows):
+        s[i] = row
+    cam = gpu.camera_with_config(cfg)
+    S = 6
+    ref = oracle_port.render(s, cam, W, H, S, 2, 5, 0)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, s, cam, W, H) as r:
+        assert r.scene_layout()["embed_ok"] == 0, label
+        r.render(5, 0, S, flags | gpu.CODEGEN_PRECOMPILED)
+        img_pre, st_pre = r.resolve(), r.stats()
+        r.clear()
+        r.render(5, 0, S, flags)
+        r.clear()
+        r.render(5, 0, S, flags)
+        img_jit, st_jit = r.resolve(), r.stats()
+        jit_ran = r.jit_info()["last_launch_jit"] == 1
+    assert np.abs(img_pre - ref).mean() < 2e-3, label
+    assert np.abs(img_jit - ref).mean() < 2e-3, label
+    assert abs(st_jit.rays - st_pre.rays) <= 2e-3 * st_pre.rays, (label, jit_ran, st_jit.rays, st_pre.rays)
+
+
 @pytest.mark.parametrize("refl", [0, 1, 2])
 def test_runtime_compilation_of_a_one_sphere_scene(gpu, oracle_port, refl):
     """The smallest layouts (one small sphere, no big one; near-only or both-roots list alone)."""
