@@ -139,7 +139,7 @@ void pack_scene(ptb_context* ctx)
     double c[3] = { 0, 0, 0 };
     int m = 0;
     for(int i = 0; i < n; ++i) {
-        if(s[i].radius <= kBigRadius) {
+        if(std::fabs(s[i].radius) <= kBigRadius) {
             c[0] += s[i].px;
             c[1] += s[i].py;
             c[2] += s[i].pz;
@@ -160,11 +160,11 @@ void pack_scene(ptb_context* ctx)
         bool have = false, same = true;
         double v = 0.0;
         for(int i = 0; i < n; ++i) {
-            if(s[i].radius <= kBigRadius) {
+            if(std::fabs(s[i].radius) <= kBigRadius) {
                 continue;
             }
             double const coord = a == 0 ? s[i].px : (a == 1 ? s[i].py : s[i].pz);
-            if(std::fabs(coord) >= 1e-3 * s[i].radius) {
+            if(std::fabs(coord) >= 1e-3 * std::fabs(s[i].radius)) {
                 continue; // the sphere extends along this axis
             }
             if(!have) {
@@ -235,7 +235,12 @@ bool near_root_only(RawSphere const& s, ptb_context const* ctx)
 PackedScene pack_geometry(ptb_context* ctx)
 {
     int const n = ctx->n;
-    std::vector<RawSphere> const& s = ctx->h_spheres;
+    // the reference only ever squares the radius (sphere.cpp:11) and normalises P - centre (hit_record.cpp:6): its sign
+    // does not matter there, and must not here, where the normal is scaled by 1/R
+    std::vector<RawSphere> s = ctx->h_spheres;
+    for(RawSphere& q : s) {
+        q.radius = std::fabs(q.radius);
+    }
     double const* sh = ctx->shift;
     PackedScene out;
 
@@ -347,7 +352,15 @@ PackedScene pack_geometry(ptb_context* ctx)
     for(int i : lists[1]) {
         max_inside_radius = std::max(max_inside_radius, s[i].radius);
     }
-    out.counts.embed_ok = extent <= 8.0 && out.counts.big_both == 0 && max_inside_radius <= 1.0;
+    // ... and a sphere much smaller than the rounding noise of |o - c|^2 (1e-7 of a few units squared) would be hit by
+    // rays that pass it at several radii: the plain discriminant needs r >= 1e-3
+    double min_radius = 1.0;
+    for(int i = 0; i < n; ++i) {
+        if(s[i].radius > 0.0) {
+            min_radius = std::min(min_radius, s[i].radius);
+        }
+    }
+    out.counts.embed_ok = extent <= 8.0 && out.counts.big_both == 0 && max_inside_radius <= 1.0 && min_radius >= 1e-3;
     if(!out.counts.embed_ok) {
         // the paired and the axis tests exist for the index-in-key kernels only: they have no exact self-sphere root
         out.counts.pair_mask = 0;
@@ -382,9 +395,14 @@ PackedScene pack_geometry(ptb_context* ctx)
             g.cy = static_cast<float>(y);
             g.cz = static_cast<float>(z);
             g.r2 = static_cast<float>(R * R);
+            if(!(g.r2 > 0.0f)) {
+                // a sphere of radius 0 (or one whose r^2 underflows binary32) is never hit in the reference either -- its
+                // discriminant is -|perp|^2 -- but in binary32 the rounding noise of that difference is not: say "never"
+                g.r2 = -1.0e30f;
+            }
             out.small_geo.push_back(g);
         }
-        double const inv_r = R != 0.0 ? 1.0 / R : 0.0;
+        double const inv_r = R > 1e-30 ? 1.0 / R : 1.0;
         double const p = std::max({ s[i].cr, s[i].cg, s[i].cb });
         double const inv_p = p > 0.0 ? 1.0 / p : 0.0;
         float4 a, b, c, d;

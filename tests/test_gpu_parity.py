@@ -433,6 +433,37 @@ def _inside_scenes(gpu):
     return W, H, out
 
 
+def test_degenerate_radii(gpu, oracle_port):
+    """Radius 0: never hit in the reference (discriminant -|perp|^2), so never hit here -- binary32 rounding noise must
+    not turn a point into a target (it did: NaN pixels, found by dev/fuzz_scenes.py).  Negative radius: the reference
+    only squares it and normalises P - centre, so it renders like |r|."""
+    W, H, S = 64, 48, 4
+    sph, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    point = np.zeros(1, dtype=gpu.SPHERE_DTYPE)
+    point[0] = (0.0, (0.0, 0.0, -1.0), (1e6, 1e6, 1e6), (1.1, 1.1, 1.1), 2, 0)
+    ref = oracle_port.render(point, cam, W, H, S, 2, 3, 0)
+    for flags in (gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL,
+                  gpu.PRECISION_FP32 | gpu.VARIANT_WAVEFRONT):
+        with make_renderer(gpu, point, cam, W, H) as r:
+            r.render(3, 0, S, flags)
+            acc, img = r.download_accum(), r.resolve()
+        assert np.isfinite(acc).all() and np.all(acc[:, 3] == S)
+        assert np.abs(img - ref).max() < 1e-5  # sky everywhere
+    neg = sph.copy()
+    neg["radius"][1:] = -neg["radius"][1:]
+    ref = oracle_port.render(neg, cam, W, H, S, 2, 3, 0)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(3, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
+        img_pos, lay_pos = r.resolve(), r.scene_layout()
+    with make_renderer(gpu, neg, cam, W, H) as r:
+        r.render(3, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
+        img_neg, lay_neg = r.resolve(), r.scene_layout()
+    assert lay_pos == lay_neg
+    assert np.array_equal(img_pos, img_neg)
+    assert np.abs(img_neg - ref).mean() < 2e-3
+
+
 @pytest.mark.parametrize("which", [0, 1, 2])
 def test_rays_inside_large_spheres_take_the_exact_self_roots(gpu, oracle_port, which):
     W, H, scenes = _inside_scenes(gpu)
