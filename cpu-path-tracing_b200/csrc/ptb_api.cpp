@@ -802,6 +802,17 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
             ctx->have_scene = false;
             return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: reflection must be 0 (diffuse), 1 (specular) or 2 (dielectric)");
         }
+        // radius, position, emission, colour: the reference would render NaN pixels from a non-finite one; here it would
+        // also reach the host-side packing (frame choice, hierarchy build), so it is an argument error
+        double v[10];
+        std::memcpy(v, &ctx->h_spheres[i], sizeof(v));
+        for(double x : v) {
+            if(!std::isfinite(x)) {
+                ctx->h_spheres.clear();
+                ctx->have_scene = false;
+                return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: a sphere holds a non-finite number");
+            }
+        }
     }
     ctx->n = static_cast<int>(count);
     if(count > ctx->d_spheres_cap) {
@@ -836,6 +847,15 @@ int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
     if(camera == nullptr || bytes != PTB_CAMERA_BYTES) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_camera: need a 176-byte pt::camera");
     }
+    {
+        double v[PTB_CAMERA_BYTES / sizeof(double)];
+        std::memcpy(v, camera, sizeof(v));
+        for(double x : v) {
+            if(!std::isfinite(x)) {
+                return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_camera: the camera holds a non-finite number");
+            }
+        }
+    }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::memcpy(static_cast<void*>(&ctx->h_camera), camera, sizeof(RawCamera));
     PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_camera, &ctx->h_camera, sizeof(RawCamera), cudaMemcpyHostToDevice, ctx->stream));
@@ -852,7 +872,11 @@ int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8)
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
-    if(cam8 == nullptr || (cam8[3] == 0.0 && cam8[4] == 0.0 && cam8[5] == 0.0)) {
+    bool finite8 = cam8 != nullptr;
+    for(int i = 0; finite8 && i < 8; ++i) {
+        finite8 = std::isfinite(cam8[i]);
+    }
+    if(!finite8 || (cam8[3] == 0.0 && cam8[4] == 0.0 && cam8[5] == 0.0)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_smallpt_camera: need position(3), non-zero direction(3), fov factor, push");
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -118,6 +118,9 @@ int ptb_synchronize(ptb_context* ctx);
 /* The sphere list of pt::scene (src/scene.hpp:12-16), in index order (the
  * closest-hit tie rule of src/main.cpp:35 depends on it).  `stride` >= 88.
  * count == 0 is valid (an empty pt::scene: every ray sees the sky, main.cpp:114-120).
+ * Every number must be finite (PTB_ERR_ARGUMENT otherwise); a radius of 0 is a
+ * sphere no ray hits, a negative radius counts as its magnitude (the reference
+ * only squares it, src/sphere.cpp:11).
  * More than 64 ordinary-sized spheres: a bounding-volume hierarchy is built here
  * (host side, milliseconds) for the FP32 kernels -- see PTB_ACCEL_*. */
 int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t stride);

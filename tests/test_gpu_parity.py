@@ -846,9 +846,20 @@ def test_error_behaviour(gpu):
         with pytest.raises(gpu.PtbError) as e:
             r.upload_scene(bad)
         assert e.value.code == -1
+        for field, value in (("radius", np.nan), ("position", np.inf), ("color", -np.inf), ("emission", np.nan)):
+            bad = sph.copy()
+            bad[field][2] = value
+            with pytest.raises(gpu.PtbError) as e:
+                r.upload_scene(bad)
+            assert e.value.code == -1 and "non-finite" in str(e.value)
         r.upload_scene(sph)
         with pytest.raises(gpu.PtbError) as e:
             r.set_camera(np.zeros(10))
+        assert e.value.code == -1
+        nan_cam = gpu.camera_with_config(cfg).copy()
+        nan_cam["u"][0][1] = np.nan
+        with pytest.raises(gpu.PtbError) as e:
+            r.set_camera(nan_cam)
         assert e.value.code == -1
         r.set_camera(gpu.camera_with_config(cfg))
         with pytest.raises(gpu.PtbError) as e:
