@@ -56,9 +56,12 @@ if __name__ == "__main__":
     oracle = None
     for it in (ONLY if ONLY else range(N)):
         s, cfg, cam, W, H, S, n, style, hostile = make_scene(BASE, it)
+        ns = [2, 2, 1, 3, 5][it % 5]
+        if ns > 2:
+            W, H = max(1, W // 2), max(1, H // 2)
         res, imgs = {}, {}
         with pkg.Renderer(0) as r:
-            r.upload_scene(s); r.set_camera(cam); r.set_image(W, H, 2)
+            r.upload_scene(s); r.set_camera(cam); r.set_image(W, H, ns)
             for label, flags, reps in (("sorted", F32 | pkg.VARIANT_MEGAKERNEL_SORTED | pkg.CODEGEN_PRECOMPILED, 1),
                                        ("sorted-jit", F32 | pkg.VARIANT_MEGAKERNEL_SORTED, 2),
                                        ("inplace", F32 | pkg.VARIANT_MEGAKERNEL | pkg.CODEGEN_PRECOMPILED, 1),
@@ -67,7 +70,11 @@ if __name__ == "__main__":
                 if label == "scan" and n > 700:
                     continue
                 for _ in range(reps):
-                    r.clear(); r.render(7 + it, 0, S, flags)
+                    r.clear()
+                    if label == "inplace" and S > 1:    # progressive: the same samples in two calls
+                        r.render(7 + it, 0, S // 2, flags); r.render(7 + it, S // 2, S - S // 2, flags)
+                    else:
+                        r.render(7 + it, 0, S, flags)
                 acc = r.download_accum(); st = r.stats()
                 if ONLY or label == "sorted":
                     imgs[label] = r.resolve()
@@ -76,7 +83,7 @@ if __name__ == "__main__":
             if oracle is None:
                 from oracle import Oracle
                 oracle = Oracle("port")
-            ref = oracle.render(s, cam, W, H, S, 2, 7 + it, 0)
+            ref = oracle.render(s, cam, W, H, S, ns, 7 + it, 0)
             print(f"scene {it}: n={n} style={style} hostile={hostile} {W}x{H}x{S} oracle image mean {ref.mean():.6g}")
             for label, im in imgs.items():
                 d = np.abs(im - ref)
@@ -85,19 +92,19 @@ if __name__ == "__main__":
             print("   camera config:", cfg.tolist())
             continue
         vs_oracle = ""
-        if W * H * S * 4 <= 120000:
+        if W * H * S * ns * ns <= 120000:
             if oracle is None:
                 from oracle import Oracle
                 oracle = Oracle("port")
-            ref = oracle.render(s, cam, W, H, S, 2, 7 + it, 0)
+            ref = oracle.render(s, cam, W, H, S, ns, 7 + it, 0)
             with pkg.Renderer(0) as r:
-                r.upload_scene(s); r.set_camera(cam); r.set_image(W, H, 2)
+                r.upload_scene(s); r.set_camera(cam); r.set_image(W, H, ns)
                 r.render(7 + it, 0, S, pkg.PRECISION_FP64)
                 img64 = r.resolve()
             d32, d64 = np.abs(imgs["sorted"] - ref), np.abs(img64 - ref)
             off32 = float((d32.max(axis=2) > 0.05).mean())
             off64 = float((d64.max(axis=2) > 1e-6).mean())
-            chaotic = res["sorted"][2] > 30 * W * H * S * 4   # ~100 bounces per path (mirror balls with colour > 1): FP32 cannot follow
+            chaotic = res["sorted"][2] > 30 * W * H * S * ns * ns   # ~100 bounces per path (mirror balls with colour > 1): FP32 cannot follow
             if (not chaotic and (d32.mean() > 1e-2 or off32 > 0.06)) or off64 > 0.01:
                 vs_oracle = f" ORACLE: fp32 mean|diff| {d32.mean():.2e} pixels off {off32:.3f}; fp64 mean|diff| {d64.mean():.2e} pixels off {off64:.3f}"
         ok = all(v[0] and v[1] for v in res.values()) and not vs_oracle
