@@ -1001,6 +1001,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         return PTB_OK; // the reference renders a black image for spp < 4 (main.cpp:206)
     }
     std::lock_guard<std::mutex> const turn(device_render_mutex(ctx->device));
+    ctx->last_launch_jit = false; // the FP64 and the wavefront kernels are never compiled at run time
     cudaStream_t st = ctx->stream;
     if(variant == PTB_VARIANT_WAVEFRONT && st == nullptr) {
         // CUDA graphs cannot be captured on the legacy default stream: drain it and use the private one;
