@@ -348,10 +348,14 @@ PackedScene pack_geometry(ptb_context* ctx)
     // epsilon = 1e-4 for grazing rays once r is a few units -- and inside a mirror ball a grazing ray stays grazing (a
     // camera in a r = 5 mirror ball traced 22 % more rays than the oracle's arithmetic).  The reference's glass balls have
     // r <= 0.5; one unit is the limit for the plain formulas.
-    double max_inside_radius = 0.0;
+    double max_inside_radius = 0.0, min_inside_radius = 1.0;
     for(int i : lists[1]) {
         max_inside_radius = std::max(max_inside_radius, s[i].radius);
+        min_inside_radius = std::min(min_inside_radius, s[i].radius);
     }
+    // At the other end, rays bouncing INSIDE a ball only some tens of epsilon across (a r = 0.006 mirror ball within the
+    // lens' reach: 1.8 % more mirror hits than the FP64 kernel, whose counts the exact-self-root path reproduces to the
+    // last ray) are decided by how a near-grazing chord of length ~epsilon is rounded: r >= 0.05 = 500 epsilon.
     // ... and a sphere much smaller than the rounding noise of |o - c|^2 (1e-7 of a few units squared) would be hit by
     // rays that pass it at several radii: the plain discriminant needs r >= 1e-3
     double min_radius = 1.0;
@@ -360,7 +364,8 @@ PackedScene pack_geometry(ptb_context* ctx)
             min_radius = std::min(min_radius, s[i].radius);
         }
     }
-    out.counts.embed_ok = extent <= 8.0 && out.counts.big_both == 0 && max_inside_radius <= 1.0 && min_radius >= 1e-3;
+    out.counts.embed_ok = extent <= 8.0 && out.counts.big_both == 0 && max_inside_radius <= 1.0 && min_inside_radius >= 0.05 &&
+                          min_radius >= 1e-3;
     if(!out.counts.embed_ok) {
         // the paired and the axis tests exist for the index-in-key kernels only: they have no exact self-sphere root
         out.counts.pair_mask = 0;
