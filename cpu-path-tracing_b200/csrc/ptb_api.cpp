@@ -18,10 +18,11 @@
 #include <string>
 #include <vector>
 
-// The precompiled FP32 kernels read the packed scene from ONE __constant__ symbol per device (ptb_f32.cu: c_scene), filled
-// stream-ordered at the start of every render.  Two contexts on the same GPU driven from two host threads would overwrite
-// it under each other's running kernel; rendering calls are blocking and each fills the whole GPU anyway, so they simply
-// take turns.
+// The PRECOMPILED FP32 kernels read the packed sphere lists from ONE __constant__ symbol per device (ptb_f32.cu: c_scene),
+// filled stream-ordered at the start of every render.  Two contexts on the same GPU driven from two host threads would
+// overwrite it under each other's running kernel, so those launches take turns (the lock is held until the kernel is done).
+// Everything else -- the run-time compiled kernels (coefficients as literals, cameras in the kernel argument) and the FP64
+// kernels (scene in per-context global memory) -- shares nothing and does not lock.
 static std::mutex& device_render_mutex(int device)
 {
     static std::mutex m[64];
@@ -51,6 +52,7 @@ struct ptb_context
     bool have_sbcam = false;
     double* d_sbcam8 = nullptr;
     ConstSceneF32 cs{};
+    CameraPair cams{}; // both cameras in the shifted FP32 frame: a kernel argument, not part of the constant block
     double shift[3] = { 0, 0, 0 };
     SceneCounts counts{};
     SmallGeo* d_small = nullptr;
@@ -459,7 +461,7 @@ void pack_camera(ptb_context* ctx)
 {
     RawCamera const& c = ctx->h_camera;
     double const* sh = ctx->shift;
-    CameraF32& o = ctx->cs.cam;
+    CameraF32& o = ctx->cams.cam;
     o.px = static_cast<float>(c.pos[0] - sh[0]);
     o.py = static_cast<float>(c.pos[1] - sh[1]);
     o.pz = static_cast<float>(c.pos[2] - sh[2]);
@@ -478,7 +480,7 @@ void pack_camera(ptb_context* ctx)
     o.sub_len = ctx->ns > 0 ? static_cast<float>(1.0 / ctx->ns) : 0.0f;
 
     // sandbox/main.cpp:235-237: cam.d normalised, cx = (w * fov / h, 0, 0), cy = norm(cx x d) * fov
-    SmallptCamF32& sbc = ctx->cs.sbcam;
+    SmallptCamF32& sbc = ctx->cams.sbcam;
     sbc = SmallptCamF32{};
     if(ctx->have_sbcam && ctx->width > 0) {
         double const* c8 = ctx->sb_cam8;
@@ -600,6 +602,16 @@ int rebuild_device_scene(ptb_context* ctx)
     }
     PTB_CUDA(ctx, cudaStreamSynchronize(st)); // ps goes out of scope
     return PTB_OK;
+}
+
+// rebuild_device_scene for callers that already HAVE a scene (camera / image changes): a failure invalidates it
+int rebuild_or_invalidate(ptb_context* ctx)
+{
+    int const rc = rebuild_device_scene(ctx);
+    if(rc != PTB_OK) {
+        ctx->have_scene = false;
+    }
+    return rc;
 }
 
 ShadePlanes shade_planes(ptb_context* ctx)
@@ -796,6 +808,9 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need spheres of stride >= 88 bytes (at most 2^24)");
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // from here until everything derived from the new list is on the device there is NO usable scene: a CUDA failure
+    // half way (out of memory on a re-upload) must not leave the previous upload's flag over new counts and freed buffers
+    ctx->have_scene = false;
     ctx->h_spheres.resize(count);
     auto const* src = static_cast<unsigned char const*>(spheres);
     for(size_t i = 0; i < count; ++i) {
@@ -831,7 +846,6 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
         PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_spheres, ctx->h_spheres.data(), count * sizeof(RawSphere),
                                       cudaMemcpyHostToDevice, ctx->stream));
     }
-    ctx->have_scene = true;
     {
         // first guess for the sorted megakernel: surface seen by a ray ~ radius^2, walls (huge spheres) capped
         double w[3] = { 0.0, 0.0, 0.0 };
@@ -841,7 +855,9 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
         }
         ctx->inline_material = w[1] >= w[0] ? 1 : 0;
     }
-    return rebuild_device_scene(ctx);
+    int const rc = rebuild_device_scene(ctx);
+    ctx->have_scene = rc == PTB_OK;
+    return rc;
 }
 
 int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
@@ -867,7 +883,7 @@ int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_camera = true;
     if(ctx->have_scene) {
-        return rebuild_device_scene(ctx);
+        return rebuild_or_invalidate(ctx);
     }
     return PTB_OK;
 }
@@ -893,7 +909,7 @@ int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8)
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_sbcam = true;
     if(ctx->have_scene) {
-        return rebuild_device_scene(ctx);
+        return rebuild_or_invalidate(ctx);
     }
     return PTB_OK;
 }
@@ -938,7 +954,7 @@ int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
         ctx->ext_accum_bytes = 0;
     }
     if(ctx->have_scene && ctx->have_sbcam) {
-        int const rc = rebuild_device_scene(ctx); // near-root-only classification depends on the aspect ratio
+        int const rc = rebuild_or_invalidate(ctx); // near-root-only classification depends on the aspect ratio
         if(rc != PTB_OK) {
             return rc;
         }
@@ -1005,7 +1021,6 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         ctx->stats.last_render_ms = 0.0;
         return PTB_OK; // the reference renders a black image for spp < 4 (main.cpp:206)
     }
-    std::lock_guard<std::mutex> const turn(device_render_mutex(ctx->device));
     ctx->last_launch_jit = false; // the FP64 and the wavefront kernels are never compiled at run time
     cudaStream_t st = ctx->stream;
     if(variant == PTB_VARIANT_WAVEFRONT && st == nullptr) {
@@ -1043,6 +1058,11 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         }
     }
 
+    // only a launch that reads the per-device constant symbol has to take turns with other contexts on this GPU
+    std::unique_lock<std::mutex> turn(device_render_mutex(ctx->device), std::defer_lock);
+    if(precision == PTB_PRECISION_FP32 && jit_kernel == nullptr) {
+        turn.lock();
+    }
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     if(precision == PTB_PRECISION_FP64) {
         if(ctx->d_accum64 == nullptr) {
@@ -1063,8 +1083,11 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         launches = 1;
     }
     else {
-        PTB_CUDA(ctx, upload_const_scene(ctx->cs, st));
+        if(jit_kernel == nullptr) {
+            PTB_CUDA(ctx, upload_const_scene(ctx->cs, st));
+        }
         RenderParamsF32 p{};
+        p.cams = ctx->cams;
         p.key = key;
         p.first_sample = first_sample;
         p.samples = samples_per_subpixel;
@@ -1112,7 +1135,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         else if(variant == PTB_VARIANT_MEGAKERNEL_SORTED) {
             ctx->last_launch_jit = jit_kernel != nullptr;
             if(jit_kernel != nullptr) {
-                PTB_CUDA(ctx, ctx->jit.launch(*jit_kernel, p, ctx->cs, ctx->sm_count, st, &launches));
+                PTB_CUDA(ctx, ctx->jit.launch(*jit_kernel, p, ctx->sm_count, st, &launches));
             }
             else {
                 PTB_CUDA(ctx, launch_megakernel_sorted(p, ctx->counts, ctx->sm_count, st, &launches, sorted_inline));
@@ -1121,7 +1144,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         else {
             ctx->last_launch_jit = jit_kernel != nullptr;
             if(jit_kernel != nullptr) {
-                PTB_CUDA(ctx, ctx->jit.launch(*jit_kernel, p, ctx->cs, ctx->sm_count, st, &launches));
+                PTB_CUDA(ctx, ctx->jit.launch(*jit_kernel, p, ctx->sm_count, st, &launches));
             }
             else {
                 PTB_CUDA(ctx, launch_megakernel(p, ctx->counts, ctx->sm_count, st, &launches, smallpt));
@@ -1371,10 +1394,13 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
        radiance_out == nullptr || count > (1u << 30)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: null pointer");
     }
-    std::lock_guard<std::mutex> const turn(device_render_mutex(ctx->device));
     uint32_t const precision = flags & PTB_PRECISION_MASK;
     if(precision != PTB_PRECISION_FP32 && precision != PTB_PRECISION_FP64) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_samples: unknown flags");
+    }
+    std::unique_lock<std::mutex> turn(device_render_mutex(ctx->device), std::defer_lock);
+    if(precision == PTB_PRECISION_FP32) {
+        turn.lock(); // the FP32 probe is a precompiled kernel: it reads the per-device constant symbol
     }
     for(size_t i = 0; i < count; ++i) {
         if(x[i] >= static_cast<uint32_t>(ctx->width) || y[i] >= static_cast<uint32_t>(ctx->height) ||
@@ -1432,6 +1458,7 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
     q.radiance = d_rad;
     q.ray = d_ray;
     q.draws = d_draws;
+    q.cams = ctx->cams;
     if(precision == PTB_PRECISION_FP64) {
         if(smallpt) {
             PTB_CUDA_T(launch_smallpt_probe_f64(q, ctx->d_spheres, ctx->n, ctx->d_sbcam8, st));

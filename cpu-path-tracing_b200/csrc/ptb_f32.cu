@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kMegaThreads) probe_f32_kernel(ProbeParams con
     uint32_t const slot = ((y * q.width + x) * q.ns + sy) * q.ns + sx;
     PathF32 p;
     p.rng = rng_open(q.key, slot, q.sample[i]);
-    Integ::generate(p, x, y, sx, sy);
+    Integ::generate(p, q.cams, x, y, sx, sy);
     if(q.ray != nullptr) {
         q.ray[6 * i + 0] = p.ox;
         q.ray[6 * i + 1] = p.oy;

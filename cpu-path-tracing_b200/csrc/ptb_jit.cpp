@@ -36,8 +36,6 @@ struct Api
     CUresult (*ModuleLoadData)(CUmodule*, void const*) = nullptr;
     CUresult (*ModuleUnload)(CUmodule) = nullptr;
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, char const*) = nullptr;
-    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, char const*) = nullptr;
-    CUresult (*MemcpyHtoDAsync)(CUdeviceptr, void const*, size_t, CUstream) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
                              void**) = nullptr;
     CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
@@ -81,8 +79,7 @@ Api& api()
                   sym(x.nvrtc, "nvrtcGetCUBIN", x.GetCUBIN) && sym(x.nvrtc, "nvrtcGetProgramLogSize", x.GetProgramLogSize) &&
                   sym(x.nvrtc, "nvrtcGetProgramLog", x.GetProgramLog);
         ok = ok && sym(x.cuda, "cuModuleLoadData", x.ModuleLoadData) && sym(x.cuda, "cuModuleUnload", x.ModuleUnload) &&
-             sym(x.cuda, "cuModuleGetFunction", x.ModuleGetFunction) && sym(x.cuda, "cuModuleGetGlobal_v2", x.ModuleGetGlobal) &&
-             sym(x.cuda, "cuMemcpyHtoDAsync_v2", x.MemcpyHtoDAsync) && sym(x.cuda, "cuLaunchKernel", x.LaunchKernel) &&
+             sym(x.cuda, "cuModuleGetFunction", x.ModuleGetFunction) && sym(x.cuda, "cuLaunchKernel", x.LaunchKernel) &&
              sym(x.cuda, "cuOccupancyMaxActiveBlocksPerMultiprocessor", x.OccupancyMaxActiveBlocks) &&
              sym(x.cuda, "cuGetErrorString", x.GetErrorString);
         x.ok = ok;
@@ -161,7 +158,6 @@ std::string JitCache::translation_unit(ConstSceneF32 const& cs, SceneCounts cons
     tu += "// generated by ptb_jit.cpp: a megakernel with this scene's coefficients as literals\n";
     tu += "#define PTB_JIT_SCENE_INIT " + init + "\n";
     tu += "#include \"ptb_kernels.h\"\n#include \"ptb_path_f32.cuh\"\n";
-    tu += "namespace ptb { __constant__ ConstSceneF32 c_scene; }\n";
     tu += kind == kSorted ? "#include \"ptb_mega_sorted.cuh\"\n" : "#include \"ptb_mega_inplace.cuh\"\n";
     return tu;
 }
@@ -202,21 +198,16 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
     push(cs.axis_coef, static_cast<size_t>(2 * nb) * sizeof(float));
     ++clock_;
     auto it = cache_.find(key);
+    bool const seen_before = it != cache_.end();
     if(it != cache_.end() && !it->second.pending) {
         it->second.last_use = clock_;
         return it->second.failed ? nullptr : &it->second;
     }
-    if(it == cache_.end() && !eager) {
-        JitKernel seen;
-        seen.pending = true;
-        seen.last_use = clock_;
-        cache_[key] = seen; // compile when it comes back
-        return nullptr;
-    }
     if(it != cache_.end()) {
         cache_.erase(it);
     }
-    // room: unload the least recently used module
+    // room (for a compiled module or a "seen once" marker alike -- an animation whose scene changes every frame must
+    // not grow the map): drop the least recently used entry
     while(cache_.size() >= kMaxModules) {
         auto victim = cache_.begin();
         for(auto j = cache_.begin(); j != cache_.end(); ++j) {
@@ -228,6 +219,13 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
             api().ModuleUnload(static_cast<CUmodule>(victim->second.module));
         }
         cache_.erase(victim);
+    }
+    if(!seen_before && !eager) {
+        JitKernel seen;
+        seen.pending = true;
+        seen.last_use = clock_;
+        cache_[key] = seen; // compile when it comes back
+        return nullptr;
     }
 
     Api& a = api();
@@ -254,8 +252,7 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
     if(a.CreateProgram(&prog, tu.c_str(), "ptb_jit_tu.cu", kJitHeaderCount, kJitHeaderSources, kJitHeaderNames) != NVRTC_SUCCESS) {
         return fail("nvrtcCreateProgram failed");
     }
-    std::string const var = "&ptb::c_scene";
-    if(a.AddNameExpression(prog, name.c_str()) != NVRTC_SUCCESS || a.AddNameExpression(prog, var.c_str()) != NVRTC_SUCCESS) {
+    if(a.AddNameExpression(prog, name.c_str()) != NVRTC_SUCCESS) {
         return fail("nvrtcAddNameExpression failed");
     }
     char const* opts[] = { "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo" };
@@ -270,8 +267,7 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
         return fail("nvrtcCompileProgram failed: " + log.substr(0, 2000));
     }
     char const* lowered_fn = nullptr;
-    char const* lowered_var = nullptr;
-    if(a.GetLoweredName(prog, name.c_str(), &lowered_fn) != NVRTC_SUCCESS || a.GetLoweredName(prog, var.c_str(), &lowered_var) != NVRTC_SUCCESS) {
+    if(a.GetLoweredName(prog, name.c_str(), &lowered_fn) != NVRTC_SUCCESS) {
         return fail("nvrtcGetLoweredName failed for " + name);
     }
     size_t bytes = 0;
@@ -297,14 +293,6 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
     if((e = a.ModuleGetFunction(&fn, mod, lowered_fn)) != CUDA_SUCCESS) {
         return cu_fail("cuModuleGetFunction", e);
     }
-    CUdeviceptr dptr = 0;
-    size_t dbytes = 0;
-    if((e = a.ModuleGetGlobal(&dptr, &dbytes, mod, lowered_var)) != CUDA_SUCCESS) {
-        return cu_fail("cuModuleGetGlobal", e);
-    }
-    if(dbytes != sizeof(ConstSceneF32)) {
-        return fail("the compiled module's c_scene has an unexpected size");
-    }
     int per_sm = 0;
     if((e = a.OccupancyMaxActiveBlocks(&per_sm, fn, 128, 0)) != CUDA_SUCCESS) {
         return cu_fail("cuOccupancyMaxActiveBlocksPerMultiprocessor", e);
@@ -312,8 +300,6 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
     a.DestroyProgram(&prog);
     prog = nullptr;
     k.function = fn;
-    k.c_scene = dptr;
-    k.c_scene_bytes = dbytes;
     k.blocks_per_sm = per_sm < 1 ? 1 : per_sm;
     k.last_use = clock_;
     compile_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -322,18 +308,14 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
     return &ins.first->second;
 }
 
-cudaError_t JitCache::launch(JitKernel const& k, RenderParamsF32 const& p, ConstSceneF32 const& cs, int sm_count, cudaStream_t stream,
-                             int* launches)
+cudaError_t JitCache::launch(JitKernel const& k, RenderParamsF32 const& p, int sm_count, cudaStream_t stream, int* launches)
 {
     Api& a = api();
     cudaError_t ce = cudaMemsetAsync(&p.counters->tile_cursor, 0, sizeof(unsigned long long), stream);
     if(ce != cudaSuccess) {
         return ce;
     }
-    // camera and the rest of the constant block of THIS module (the coefficients in it are not read by the kernel)
-    if(a.MemcpyHtoDAsync(static_cast<CUdeviceptr>(k.c_scene), &cs, sizeof(ConstSceneF32), reinterpret_cast<CUstream>(stream)) != CUDA_SUCCESS) {
-        return cudaErrorUnknown;
-    }
+    // nothing else to stage: the coefficients are literals in the code, the cameras ride in the kernel argument
     unsigned long long blocks = static_cast<unsigned long long>(sm_count) * static_cast<unsigned long long>(k.blocks_per_sm);
     unsigned long long const needed = (static_cast<unsigned long long>(p.ntiles) + 3ull) / 4ull; // 4 warps per block
     blocks = blocks > needed ? needed : blocks;

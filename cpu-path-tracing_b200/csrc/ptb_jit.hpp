@@ -26,8 +26,6 @@ struct JitKernel
 {
     void* module = nullptr;          // CUmodule
     void* function = nullptr;        // CUfunction
-    unsigned long long c_scene = 0;  // CUdeviceptr of the module's ptb::c_scene
-    size_t c_scene_bytes = 0;
     int blocks_per_sm = 0;
     bool failed = false;             // negative cache entry: do not try this key again
     bool pending = false;            // seen once, not compiled yet
@@ -52,8 +50,7 @@ public:
     enum Kind { kSorted = 0, kInPlacePt = 1, kInPlaceSmallpt = 2 };
     JitKernel const* get(ConstSceneF32 const& cs, SceneCounts const& counts, Kind kind, int inline_material, bool eager);
     // Launch it: same grid policy and semantics as launch_megakernel_sorted.
-    cudaError_t launch(JitKernel const& k, RenderParamsF32 const& p, ConstSceneF32 const& cs, int sm_count, cudaStream_t stream,
-                       int* launches);
+    cudaError_t launch(JitKernel const& k, RenderParamsF32 const& p, int sm_count, cudaStream_t stream, int* launches);
 
     bool available();                 // libnvrtc + libcuda found and not disabled (PTB_JIT=0)
     int compiled() const { return compiled_; }

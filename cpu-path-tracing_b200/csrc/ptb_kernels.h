@@ -37,6 +37,7 @@ struct RenderParamsF32
     GeoLists geo;           // global-memory geometry lists (generic variant)
     int n_total;
     uint32_t key_mask;      // ~(2^kIdBits - 1), handed over as DATA so that it lives in a register (see closest_hit)
+    CameraPair cams;        // thin-lens camera of src/main.cpp and the sandbox's pinhole camera, shifted FP32 frame
 };
 
 #ifndef __CUDACC_RTC__ // everything below is host-side; the run-time compiler only needs the records above
@@ -102,6 +103,7 @@ struct ProbeParams
     double* radiance; // [count*3]
     double* ray;      // [count*6] or nullptr
     uint32_t* draws;  // [count] or nullptr
+    CameraPair cams;  // FP32 probe only
 };
 cudaError_t launch_probe_f32(ProbeParams const& p, SceneCounts const& c, ShadePlanes const& shade, GeoLists const& geo,
                              cudaStream_t stream, bool smallpt);

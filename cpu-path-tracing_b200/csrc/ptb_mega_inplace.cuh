@@ -34,18 +34,18 @@ constexpr uint32_t kVoidSlot = 0xFFFFFFFFu;
 struct IntegratorPt
 {
     static constexpr bool kSplit = false;
-    __device__ static __forceinline__ void generate(PathF32& g, uint32_t x, uint32_t y, uint32_t sx, uint32_t sy)
+    __device__ static __forceinline__ void generate(PathF32& g, CameraPair const& cams, uint32_t x, uint32_t y, uint32_t sx, uint32_t sy)
     {
-        gen_primary(g, c_scene.cam, x, y, sx, sy);
+        gen_primary(g, cams.cam, x, y, sx, sy);
     }
     __device__ static __forceinline__ float ring_word(PathF32 const& g)
     {
         return g.len;
     }
-    __device__ static __forceinline__ void unpack(PathF32& p, float word)
+    __device__ static __forceinline__ void unpack(PathF32& p, CameraPair const& cams, float word)
     {
         p.len = word;
-        p.oz = c_scene.cam.pz;
+        p.oz = cams.cam.pz;
     }
     __device__ static __forceinline__ bool bounce(PathF32& p, bool hit, float t, int id, ShadePlanes const& sp,
                                                   BounceCounters& cnt, SplitStack&)
@@ -58,15 +58,15 @@ struct IntegratorPt
 struct IntegratorSmallpt
 {
     static constexpr bool kSplit = true;
-    __device__ static __forceinline__ void generate(PathF32& g, uint32_t x, uint32_t y, uint32_t sx, uint32_t sy)
+    __device__ static __forceinline__ void generate(PathF32& g, CameraPair const& cams, uint32_t x, uint32_t y, uint32_t sx, uint32_t sy)
     {
-        gen_smallpt(g, c_scene.sbcam, x, y, sx, sy);
+        gen_smallpt(g, cams.sbcam, x, y, sx, sy);
     }
     __device__ static __forceinline__ float ring_word(PathF32 const& g)
     {
         return g.oz;
     }
-    __device__ static __forceinline__ void unpack(PathF32& p, float word)
+    __device__ static __forceinline__ void unpack(PathF32& p, CameraPair const&, float word)
     {
         p.len = 1.0f;
         p.oz = word;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                 g.rng.state = g.rng.inc = 0u;
                 if(gen_slot != kVoidSlot) {
                     g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
-                    Integ::generate(g, gen_x, gen_y, gen_sx, gen_sy);
+                    Integ::generate(g, prm.cams, gen_x, gen_y, gen_sx, gen_sy);
                 }
                 uint32_t const w = (ring_head + lane) & (kRingSize - 1);
                 ring.a[w] = make_float4(g.ox, g.oy, g.dx, g.dy);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kMegaThreads) mega_kernel(RenderParamsF32 cons
                     p.dx = ea.z;
                     p.dy = ea.w;
                     p.dz = eb.x;
-                    Integ::unpack(p, eb.y);
+                    Integ::unpack(p, prm.cams, eb.y);
                     p.rng.state = __float_as_uint(eb.z);
                     p.rng.inc = __float_as_uint(eb.w);
                     p.tr = p.tg = p.tb = 1.0f;

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     if(lane < gen_valid) {
                         PathF32 g;
                         g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
-                        gen_primary(g, c_scene.cam, gen_x, gen_y, gen_sx, gen_sy);
+                        gen_primary(g, prm.cams.cam, gen_x, gen_y, gen_sx, gen_sy);
                         uint32_t const w = ready_base + ((ready_head + lane * 16u) & kRingMask);
                         sts128(w, g.ox, g.oy, g.oz, g.len);
                         sts128(w + kPlaneBytes, g.dx, g.dy, g.dz, __uint_as_float(gen_slot));

@@ -468,7 +468,8 @@ __device__ __forceinline__ bool closest_hit(Scene const& cs, GeoLists const& gl,
     uint32_t best = kNoHitBits;
     int id = -1;
     if constexpr(!Shape::generic) {
-        static_assert(Shape::total <= (1 << kIdBits), "list position does not fit the key");
+        // only the index-in-key kernels are limited by the key's spare bits; full-precision keys carry the id separately
+        static_assert(!Shape::embed || Shape::total <= (1 << kIdBits), "list position does not fit the key");
         constexpr uint32_t keep = Shape::embed ? ~((1u << kIdBits) - 1u) : 0xFFFFFFFFu;
         constexpr int NS = Shape::small_near + Shape::small_both;
         constexpr int NB = Shape::big_near + Shape::big_both;

@@ -91,11 +91,19 @@ struct SmallptCamF32
     float pad_[3];
 };
 
-// Everything the FP32 kernels read through the constant cache.
-struct ConstSceneF32
+// Both cameras as the FP32 kernels take them: a KERNEL ARGUMENT (RenderParamsF32 / ProbeParams), so that nothing a
+// render reads except the precompiled kernels' sphere coefficients lives in a per-device __constant__ symbol -- the
+// run-time compiled kernels (coefficients as literals) read no shared symbol at all, and contexts on one GPU that use
+// them do not have to take turns.
+struct CameraPair
 {
     CameraF32 cam;
     SmallptCamF32 sbcam;
+};
+
+// Everything the FP32 kernels read through the constant cache.
+struct ConstSceneF32
+{
     int n_small_near; // small spheres tested at the near root only
     int n_small;      // all small spheres (near-only first)
     int n_big_near;

@@ -69,9 +69,9 @@ __device__ __forceinline__ void wf_load(WfStream const& s, uint32_t i, PathF32& 
     p.dx = b.x;
     p.dy = b.y;
     p.dz = b.z;
-    int const packed = __float_as_int(b.w); // depth (< 2^8) | (last + 1) << 8
-    p.depth = packed & 0xFF;
-    p.last = (packed >> 8) - 1;
+    uint32_t const packed = __float_as_uint(b.w); // depth (< 2^8) | (last + 1) << 8, unsigned: list positions reach 2^24
+    p.depth = static_cast<int>(packed & 0xFFu);
+    p.last = static_cast<int>(packed >> 8) - 1;
     p.tr = c.x;
     p.tg = c.y;
     p.tb = c.z;
@@ -86,7 +86,7 @@ __device__ __forceinline__ void wf_load(WfStream const& s, uint32_t i, PathF32& 
 __device__ __forceinline__ void wf_store(WfStream const& s, uint32_t i, PathF32 const& p, uint32_t slot)
 {
     s.a[i] = make_float4(p.ox, p.oy, p.oz, p.len);
-    s.b[i] = make_float4(p.dx, p.dy, p.dz, __int_as_float(p.depth | ((p.last + 1) << 8)));
+    s.b[i] = make_float4(p.dx, p.dy, p.dz, __uint_as_float(static_cast<uint32_t>(p.depth) | (static_cast<uint32_t>(p.last + 1) << 8)));
     s.c[i] = make_float4(p.tr, p.tg, p.tb, __uint_as_float(p.rng.state));
     s.d[i] = make_float4(p.er, p.eg, p.eb, __uint_as_float(p.rng.inc));
     s.slot[i] = slot;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kWfThreads) wf_regen_kernel(WavefrontState con
         p.rng = rng_open(prm.key, slot, prm.first_sample + sample);
         uint32_t x, y, sx, sy;
         slot_coords(slot, prm.width, prm.ns, x, y, sx, sy);
-        gen_primary(p, c_scene.cam, x, y, sx, sy);
+        gen_primary(p, prm.cams.cam, x, y, sx, sy);
         wf_store(w.active[cur], base + j, p, slot);
     }
 }

@@ -21,13 +21,12 @@ def initialiser(ns, nb):
 
 def compile_kernel(label, header, name, ns, nb, out=None):
     tu = ("#define PTB_JIT_SCENE_INIT " + initialiser(ns, nb) + "\n#include \"ptb_kernels.h\"\n#include \"ptb_path_f32.cuh\"\n"
-          "namespace ptb { __constant__ ConstSceneF32 c_scene; }\n#include \"" + header + "\"\n").encode()
+          "#include \"" + header + "\"\n").encode()
     prog = ctypes.c_void_p()
     hs = (ctypes.c_char_p * len(HEADERS))(*srcs)
     hn = (ctypes.c_char_p * len(HEADERS))(*[h.encode() for h in HEADERS])
     assert n.nvrtcCreateProgram(ctypes.byref(prog), tu, b"ptb_jit_tu.cu", len(HEADERS), hs, hn) == 0
     assert n.nvrtcAddNameExpression(prog, name) == 0
-    assert n.nvrtcAddNameExpression(prog, b"&ptb::c_scene") == 0
     opts = (ctypes.c_char_p * 3)(b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo")
     t0 = time.time()
     rc = n.nvrtcCompileProgram(prog, 3, opts)
@@ -39,7 +38,6 @@ def compile_kernel(label, header, name, ns, nb, out=None):
         print(log.value.decode()[:3000])
     if rc == 0:
         low = ctypes.c_char_p(); n.nvrtcGetLoweredName(prog, name, ctypes.byref(low)); print("  kernel:", low.value.decode())
-        n.nvrtcGetLoweredName(prog, b"&ptb::c_scene", ctypes.byref(low)); print("  c_scene:", low.value.decode())
         n.nvrtcGetCUBINSize(prog, ctypes.byref(sz)); print("  cubin bytes", sz.value)
         if out:
             buf = ctypes.create_string_buffer(sz.value); n.nvrtcGetCUBIN(prog, buf); open(out, "wb").write(buf.raw)

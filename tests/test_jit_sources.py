@@ -25,7 +25,10 @@ def test_device_headers_compile_under_nvrtc(tmp_path):
     cubin = tmp_path / "k.cubin"
     out = subprocess.run([sys.executable, os.path.join(ROOT, "dev", "nvrtc_check.py"), str(cubin)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "mega_sorted_kernel" in out.stdout and "c_scene" in out.stdout
+    assert "mega_sorted_kernel" in out.stdout
+    # a run-time compiled kernel shares no __constant__ symbol with anybody: coefficients are literals, cameras ride in
+    # the kernel argument (so contexts on one GPU need no lock for it)
+    assert "c_scene" not in out.stdout
     assert cubin.stat().st_size > 10000
     # the point of the exercise: with literal coefficients the closest-hit scan has (almost) no constant-bank loads left
     sass = subprocess.run(["cuobjdump", "-sass", str(cubin)], capture_output=True, text=True).stdout
