@@ -119,25 +119,38 @@ class ClockSampler:
         return out
 
 
+def reference_scene(pkg_loader, scene, width, height):
+    """(spheres, camera) for the CPU arms.  The three scenes the reference ships come from the REFERENCE's own builders
+    (oracle/_ref/libptref_stock.so: ptref_scene) when that library exists, so that no code of this repo's product is in
+    the reference arm's process; the two BASELINE configs the reference has no builder for (dof_glass, spheres10k) come
+    from the host-side scene layer of this repo (no GPU code involved)."""
+    from oracle import Oracle, available
+
+    if scene in ("simple", "box", "box_mirror") and available("ref_stock"):
+        sph, _, cam = Oracle("ref_stock").scene(scene, width, height)
+        return sph, cam
+    pkg = pkg_loader()
+    spheres, cfg = pkg.builtin_scene(scene, width, height)
+    return spheres, pkg.camera_with_config(cfg)
+
+
 def cpu_reference_rate(scene, width, height, samps, kind_pref=("ref_stock", "port")):
     """Mpaths/s of the reference's CPU implementation on this box's host cores.
-    Returns (value, kind, cores, seconds, oracle-stats or None)."""
+    Returns (value, kind, cores, seconds)."""
     from oracle import Oracle, available
     from __graft_entry__ import load_package
 
-    pkg = load_package()
     cores = os.cpu_count() or 1
     paths = width * height * 4 * samps
     if scene == "smallpt":
-        spheres, cam8 = pkg.builtin_smallpt_scene()
         kind = "reference" if available("ref_sandbox") else "port"
         orc = Oracle("ref_sandbox" if kind == "reference" else "port")
+        spheres, cam8 = orc.sb_scene() if kind == "reference" else load_package().builtin_smallpt_scene()
         t0 = time.perf_counter()
         orc.sb_render(spheres, cam8, width, height, samps, mode=0, nthreads=cores)  # the program's own erand48 stream
         dt = time.perf_counter() - t0
         return paths / dt / 1e6, kind, cores, dt
-    spheres, cfg = pkg.builtin_scene(scene, width, height)  # host-side scene layer only (no GPU)
-    cam = pkg.camera_with_config(cfg)
+    spheres, cam = reference_scene(load_package, scene, width, height)
     if "ref_stock" in kind_pref and available("ref_stock"):
         orc = Oracle("ref_stock")
         t0 = time.perf_counter()
@@ -172,7 +185,7 @@ def run_reference(args, scene, width, height, spp):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    samps = 1 if scene != "spheres10k" else 1  # 4 spp per step: a bounded sample of the same frame
+    samps = 1  # 4 spp per step: a bounded sample of the same frame
     w, h = (width, height) if scene != "spheres10k" else (width // 8, height // 8)
     for _ in range(args.warmup):
         cpu_reference_rate(scene, w, h, samps)
@@ -187,7 +200,9 @@ def run_reference(args, scene, width, height, spp):
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {scene} {width}x{height} @ {spp} spp", "sample": sample},
+        "config": {"workload": f"{args.config}: {scene} {width}x{height} @ {spp} spp", "sample": sample,
+                   "note": "a RATE on a 4-spp sample of the same frame (a whole 4096-spp frame takes ~20 min on the CPU): "
+                           "the ratio to the GPU arm is a throughput ratio, not a same-work wall-clock ratio"},
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,24 +241,24 @@ def main():
     ap.add_argument("--variant", default="sorted", choices=["mega", "wavefront", "sorted"],
                     help="sorted = material-sorted megakernel (the product path); mega = in-place megakernel; wavefront")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer"],
+                    help="how the per-GPU sums travel (include/ptb200.h PTB_TRANSPORT_*)")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false",
+                    help="skip the one-frame measurements of C2, C4, C5 and SB that follow the headline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least three warm-up steps
 
-    scene, width, height, spp = CONFIGS[args.config]
-    if args.spp:
-        spp = args.spp
-    samps = spp // 4  # main.cpp:206
-
     if args.impl == "reference":
-        return run_reference(args, scene, width, height, spp)
+        scene, width, height, spp = CONFIGS[args.config]
+        return run_reference(args, scene, width, height, args.spp or spp)
 
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
 
     pkg = load_package()  # raises if libptb200.so is missing: there is no fallback
-    from cpu_path_tracing_b200.distributed import DistributedRenderer, sample_range
+    from cpu_path_tracing_b200.distributed import DistributedRenderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,149 +267,203 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    flags = pkg.PRECISION_FP32 | {"mega": pkg.VARIANT_MEGAKERNEL, "wavefront": pkg.VARIANT_WAVEFRONT,
-                                  "sorted": pkg.VARIANT_MEGAKERNEL_SORTED}[args.variant]
-
-    dr = DistributedRenderer(pkg, local, rank, world)
-    if scene == "smallpt":
-        spheres, cam = pkg.builtin_smallpt_scene()  # cam = cam8
-        args.variant = "mega"  # the sandbox integrator (splitting glass) runs on the in-place megakernel only
-        flags = pkg.PRECISION_FP32 | pkg.VARIANT_MEGAKERNEL | pkg.INTEGRATOR_SMALLPT
-        dr.setup(spheres, None, width, height, 2, smallpt_camera=cam)
-        set_camera = dr.renderer.set_smallpt_camera
-    else:
-        spheres, cfg = pkg.builtin_scene(scene, width, height)
-        cam = pkg.camera_with_config(cfg)
-        dr.setup(spheres, cam, width, height, 2)
-        set_camera = dr.renderer.set_camera
-    r = dr.renderer
+    transport = {"auto": pkg.TRANSPORT_AUTO, "nccl": pkg.TRANSPORT_NCCL, "peer": pkg.TRANSPORT_PEER}[args.transport]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident measurement ------------------------------------------------------------
-    for _ in range(args.warmup):
-        dr.step(SEED, samps, flags)
-    launches0 = r.stats().kernel_launches
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
-    for a, b in ev:
-        a.record()
-        dr.step(SEED, samps, flags)
-        b.record()
-        kernel_ms.append(r.stats().last_render_ms)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    launches = r.stats().kernel_launches - launches0
-    st = r.stats()
-    my_first, my_count = sample_range(samps, world, rank)
-    # statistics are cleared only by ptb_clear; DistributedRenderer zeroes its tensor itself, so rays and
-    # paths have accumulated over every step since setup on this rank
-    counters = torch.tensor([st.rays, st.paths], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
-    rays_per_path = float(counters[0].item() / max(counters[1].item(), 1.0))
+    def allreduce(values, op):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return [float(v) for v in t.tolist()]
 
-    paths_per_step = width * height * 4 * samps
-    value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
-
-    # ---- end to end through the C ABI with host buffers -------------------------------------------------
-    # every step: scene + camera from host memory -> device, render, reduce, image -> host memory
-    host_img = np.empty((height, width, 3), dtype=np.float64)
-    pinned = torch.empty((height, width, 3), dtype=torch.float64).pin_memory().numpy() if rank == 0 else None
-    sph_bytes = np.ascontiguousarray(spheres).view(np.uint8)
-    h2d = int(sph_bytes.nbytes + cam.nbytes)
-    d2h = int(host_img.nbytes)
-
-    def e2e_step():
-        r.upload_scene(spheres)
-        set_camera(cam)
-        dr.step(SEED, samps, flags, resolve=False)
-        if rank == 0:
-            r.resolve_into(pinned)
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_ev0, e2e_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_ev0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_ev1.record()
-    barrier()
-    e2e_ms = torch.tensor([max(e2e_ev0.elapsed_time(e2e_ev1), 0.0)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = paths_per_step * args.steps / (float(e2e_ms.item()) * 1e-3) / 1e6
-    del t0
-
-    if rank == 0:
-        jit = r.jit_info()
-        peak_tflops = r.measure_fp32_peak()
-        ostats, n_spheres = oracle_statistics(scene, width, height)
-        if ostats is None:
-            # sandbox scene: same per-operation constants, event counts from the GPU counters of this run
-            # (no sky; ~1/3 of the 10 sphere tests reach the root stage, measured on the src/ scenes)
-            rpp = rays_per_path
-            hits = {k: getattr(st, "hits_" + k) / max(st.paths, 1) for k in ("diffuse", "specular", "dielectric")}
-            fpp = (rpp * (FLOP_RAY_FIXED + n_spheres * (FLOP_TEST + 0.66 * FLOP_ROOT + 0.33 * FLOP_ROOT2)) + FLOP_SHADE * rpp
-                   + FLOP_DIFFUSE * hits["diffuse"] + FLOP_SPECULAR * hits["specular"]
-                   + (FLOP_DIELECTRIC + FLOP_REFRACT) * hits["dielectric"] + FLOP_PRIMARY)
+    def measure(cfg_name, steps, warmup, variant, headline):
+        """One workload on this job's GPUs -> dict (rank 0) with value / e2e / roofline; every rank takes part."""
+        scene, width, height, spp = CONFIGS[cfg_name]
+        if headline and args.spp:
+            spp = args.spp
+        samps = spp // 4  # main.cpp:206
+        flags = pkg.PRECISION_FP32 | {"mega": pkg.VARIANT_MEGAKERNEL, "wavefront": pkg.VARIANT_WAVEFRONT,
+                                      "sorted": pkg.VARIANT_MEGAKERNEL_SORTED}[variant]
+        dr = DistributedRenderer(pkg, local, rank, world, transport)
+        if scene == "smallpt":
+            spheres, cam = pkg.builtin_smallpt_scene()  # cam = cam8
+            variant = "mega"  # the sandbox integrator (splitting glass) runs on the in-place megakernel only
+            flags = pkg.PRECISION_FP32 | pkg.VARIANT_MEGAKERNEL | pkg.INTEGRATOR_SMALLPT
+            dr.setup(spheres, None, width, height, 2, smallpt_camera=cam)
+            set_camera = dr.renderer.set_smallpt_camera
         else:
-            fpp = flop_per_path(ostats, n_spheres)
-        # the dominant kernel = the megakernel; its average launch duration from the library's own events
-        k_ms = sum(kernel_ms) / len(kernel_ms)
-        paths_per_launch = width * height * 4 * my_count
-        achieved = paths_per_launch * fpp / (k_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"{args.config}_{args.variant}")
+            spheres, cfg = pkg.builtin_scene(scene, width, height)
+            cam = pkg.camera_with_config(cfg)
+            dr.setup(spheres, cam, width, height, 2)
+            set_camera = dr.renderer.set_camera
+        r = dr.renderer
+
+        # ---- device-resident measurement: scene, camera and accumulation buffer live in HBM -------------------------
+        for _ in range(warmup):
+            dr.step(SEED, samps, flags)
+        launches0 = r.stats().kernel_launches
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kernel_ms, resolve_ms = [], []
+        for a, b in ev:
+            a.record()
+            dr.step(SEED, samps, flags)
+            b.record()
+            st = r.stats()
+            kernel_ms.append(st.last_render_ms)
+            resolve_ms.append(st.last_resolve_ms)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        total_ms = allreduce([sum(a.elapsed_time(b) for a, b in ev)], dist.ReduceOp.MAX)[0]
+        st = r.stats()  # statistics of the LAST step (every step starts with ptb_clear)
+        launches = st.kernel_launches - launches0
+        rays, paths_traced, nd, nsp, ndi = allreduce([st.rays, st.paths, st.hits_diffuse, st.hits_specular, st.hits_dielectric],
+                                                     dist.ReduceOp.SUM)
+        paths_per_step = width * height * 4 * samps
+        rays_per_path = rays / max(paths_traced, 1.0)
+        value = paths_per_step * steps / (total_ms * 1e-3) / 1e6
+
+        # ---- end to end through the C ABI with HOST buffers ------------------------------------------------------------
+        # every step: scene + camera from host memory -> device, clear, render, sum across GPUs, image -> host memory.
+        # Image format: what the reference's writer needs.  FP64 pixels for the headline (std::vector<pt::vec3>,
+        # main.cpp:210); for the 4K workload the 8-bit image the output stage writes (ptb_resolve_rgb8 + P6: 24.9 MB, not 199).
+        use_rgb8 = width * height > 1920 * 1080
+        if use_rgb8:
+            pinned = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory().numpy() if rank == 0 else None
+        else:
+            pinned = torch.empty((height, width, 3), dtype=torch.float64).pin_memory().numpy() if rank == 0 else None
+        sph_bytes = np.ascontiguousarray(spheres).view(np.uint8)
+        h2d = int(sph_bytes.nbytes + cam.nbytes)
+        d2h = int(pinned.nbytes) if rank == 0 else 0
+
+        def e2e_step():
+            r.upload_scene(spheres)
+            set_camera(cam)
+            r.clear()
+            r.render(SEED, 0, samps, flags)
+            if rank == 0:
+                (r.resolve_rgb8_into if use_rgb8 else r.resolve_into)(pinned)
+            else:
+                r.resolve_collective()
+
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = allreduce([max(e0.elapsed_time(e1), 0.0)], dist.ReduceOp.MAX)[0]
+        e2e_value = paths_per_step * steps / (e2e_ms * 1e-3) / 1e6
+        d2h = int(allreduce([d2h], dist.ReduceOp.SUM)[0])
+
+        out = None
+        if rank == 0:
+            jit = r.jit_info()
+            comm = r.comm_info()
+            peak_tflops = r.measure_fp32_peak()
+            ostats, n_spheres = oracle_statistics(scene, width, height)
+            if ostats is None:
+                # sandbox scene: same per-operation constants, event counts from the GPU counters of this run
+                # (no sky; ~1/3 of the 10 sphere tests reach the root stage, measured on the src/ scenes)
+                rpp = rays_per_path
+                hits = {"diffuse": nd / max(paths_traced, 1), "specular": nsp / max(paths_traced, 1),
+                        "dielectric": ndi / max(paths_traced, 1)}
+                fpp = (rpp * (FLOP_RAY_FIXED + n_spheres * (FLOP_TEST + 0.66 * FLOP_ROOT + 0.33 * FLOP_ROOT2)) + FLOP_SHADE * rpp
+                       + FLOP_DIFFUSE * hits["diffuse"] + FLOP_SPECULAR * hits["specular"]
+                       + (FLOP_DIELECTRIC + FLOP_REFRACT) * hits["dielectric"] + FLOP_PRIMARY)
+            else:
+                fpp = flop_per_path(ostats, n_spheres)
+            # the dominant kernel = the megakernel; its average launch duration from the library's own events
+            k_ms = sum(kernel_ms) / len(kernel_ms)
+            paths_per_launch = st.paths  # what THIS rank's launch traced (its share of the samples)
+            achieved = paths_per_launch * fpp / (k_ms * 1e-3) / 1e12
+            out = {
+                "value": value, "ms_per_step": total_ms / steps, "Mrays_per_s": value * rays_per_path,
+                "rays_per_path": rays_per_path,
+                "config": {
+                    "workload": f"{cfg_name}: {scene} {width}x{height} @ {spp} spp "
+                                + (f"(BASELINE.json configs[{int(cfg_name[1]) - 1}])" if cfg_name[0] == "C" else "(sandbox/main.cpp, SURVEY 8 f-1)"),
+                    "variant": variant, "samples_per_subpixel": samps, "spheres": int(len(spheres)),
+                    "codegen": ("run-time compiled for this scene (NVRTC, %d ms once)" % jit["compile_ms"]) if jit["last_launch_jit"]
+                    else "precompiled",
+                    "partition": (f"samples of every sub-pixel split over {world} GPU(s) inside the library (ptb_comm_init_rank); "
+                                  f"sum + resolve over {comm['last_transport']} "
+                                  + ("(one fused reduce-scatter + resolve + gather kernel per GPU over NVLink peer mappings)"
+                                     if comm["last_transport"] == "peer" else "(ncclReduce to rank 0, then resolve)"))
+                    if world > 1 else "single GPU",
+                    "l2": "every step zeroes the accumulation buffer (133 MB at 1080p > 126 MB L2) and the kernel's inputs are "
+                          "~1 KB of constants: compute-bound, L2 state does not matter",
+                    "seed": SEED,
+                },
+                "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "image": "rgb8 (ptb_resolve_rgb8)" if use_rgb8 else "FP64 pixels (ptb_resolve)"},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "sum_resolve_ms": sum(resolve_ms) / len(resolve_ms),
+                "roofline": {
+                    "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                    "traffic": None, "flop_per_path": fpp, "kernel_ms": k_ms,
+                    "peak_source": "FFMA loop measured live on this GPU (ptb_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.45",
+                },
+            }
+            ncu = ncu_counters(cfg_name, variant)
+            if ncu is not None:
+                # counters of the SAME kernel build from its ncu capture under profiles/ (never from this run: a profiled
+                # run is not a bench run) -- executed FP32 lane-operations against the pipe's peak, DRAM bytes per launch
+                out["roofline"]["ncu"] = ncu
+                out["roofline"]["executed_frac"] = ncu.get("executed_fp32_frac")
+                out["roofline"]["traffic"] = ncu.get("dram_bytes_per_launch")
+            if scene == "spheres10k":
+                # flop_per_path is the REFERENCE's algorithm (a 10 001-sphere linear scan per ray, SURVEY.md section 8d);
+                # the kernel answers the same queries through a bounding-volume hierarchy, so achieved/peak is an
+                # equivalent-work rate (> 1 = work skipped), not a pipe fraction.  The pipe fraction of what the kernel
+                # does execute comes from its ncu capture ("executed_frac").
+                out["roofline"]["equivalent_scan_frac"] = achieved / peak_tflops
+                out["roofline"]["frac"] = out["roofline"].get("executed_frac")
+                out["roofline"]["note"] = ("closest hit through a hierarchy (PTB_ACCEL_AUTO): 'achieved' counts the reference's "
+                                           "linear scan (equivalent work); 'frac' is the executed-FP32 lane utilisation of the "
+                                           "traversal kernel from its ncu capture; latency-bound, see profiles/")
+        dr.close()
+        return out
+
+    head = measure(args.config, args.steps, args.warmup, args.variant, True)
+    parity_n = None
+    if world > 1:
+        parity_n = parity_across_ranks(pkg, dist, torch, rank, world, local, transport)
+    others = {}
+    if args.other_configs and args.config == "C3":
+        for name in ("C2", "C4", "C5", "SB"):
+            o = measure(name, 1, 3, "sorted", False)
+            if rank == 0:
+                others[name] = {k: o[k] for k in ("value", "ms_per_step", "Mrays_per_s", "rays_per_path", "e2e", "clocks",
+                                                  "sum_resolve_ms")}
+                others[name]["workload"] = o["config"]["workload"]
+                others[name]["variant"] = o["config"]["variant"]
+                others[name]["roofline"] = {k: o["roofline"].get(k) for k in ("frac", "achieved", "peak", "kernel_ms", "flop_per_path",
+                                                                               "executed_frac", "equivalent_scan_frac")}
+    if rank == 0:
+        scene, width, height, spp = CONFIGS[args.config]
         line = {
-            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "metric": "Mpaths/s", "value": head["value"], "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"{args.config}: {scene} {width}x{height} @ {spp} spp "
-                            + (f"(BASELINE.json configs[{int(args.config[1]) - 1}])" if args.config[0] == "C" else "(sandbox/main.cpp, SURVEY 8 f-1)"),
-                "variant": args.variant, "samples_per_subpixel": samps, "spheres": int(len(spheres)),
-                "codegen": ("run-time compiled for this scene (NVRTC, %d ms once)" % jit["compile_ms"]) if jit["last_launch_jit"]
-                else "precompiled",
-                "partition": f"samples of every sub-pixel split over {world} GPU(s); NCCL sum-reduce to rank 0" if world > 1
-                else "single GPU",
-                "l2": "every step zeroes the accumulation buffer (133 MB at 1080p > 126 MB L2) and the kernel's inputs are "
-                      "~1 KB of constants: compute-bound, L2 state does not matter",
-                "seed": SEED,
-            },
-            "Mrays_per_s": value * rays_per_path, "rays_per_path": rays_per_path,
-            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {
-                "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                "traffic": traffic, "flop_per_path": fpp, "kernel_ms": k_ms,
-                "peak_source": "FFMA loop measured live on this GPU (ptb_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.45",
-            },
+            "config": head["config"], "Mrays_per_s": head["Mrays_per_s"], "rays_per_path": head["rays_per_path"],
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "sum_resolve_ms": head["sum_resolve_ms"], "roofline": head["roofline"],
         }
-        if scene == "spheres10k":
-            # flop_per_path is the REFERENCE's algorithm (a 10 001-sphere linear scan per ray);
-            # the kernel answers the same queries through a bounding-volume hierarchy (~10 box pairs + ~0.6 sphere tests
-            # per ray), so "achieved" is an equivalent-work rate and may exceed the hardware peak -- not a pipe fraction
-            line["roofline"]["frac"] = None
-            line["roofline"]["equivalent_scan_frac"] = achieved / peak_tflops
-            line["roofline"]["note"] = ("closest hit through a hierarchy (PTB_ACCEL_AUTO): algorithmic flops are the reference's "
-                                        "linear scan, achieved/peak > 1 means work skipped, not a pipe utilisation")
+        if parity_n is not None:
+            line["parity_n"] = parity_n
+        if others:
+            line["other_configs"] = others
         if not args.no_cpu_baseline:
             bw, bh = (width, height) if scene != "spheres10k" else (width // 8, height // 8)
             bs = 4 if scene != "spheres10k" else 1
@@ -403,10 +472,74 @@ def main():
                                     "sample": f"{scene} {bw}x{bh} at {4 * bs} spp ({bw * bh * 4 * bs / 1e6:.1f} Mpaths, {dt:.1f} s), "
                                               f"all {cores} host threads, OpenMP dynamic rows"}
         _emit(line)
-    dr.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_counters(cfg_name, variant):
+    """Counters of the shipped kernel from its committed ncu capture (profiles/ncu_counters.json), or None when the file
+    has no entry for this workload or was taken from another build of the kernels."""
+    path = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    if not os.path.exists(path):
+        return None
+    table = json.load(open(path))
+    entry = table.get(f"{cfg_name}_{variant}")
+    if entry is None or entry.get("kernel_build") != kernel_build_id():
+        return None
+    return entry
+
+
+def kernel_build_id():
+    """Hash of the device sources: an ncu capture describes ONE build of the kernels."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "cpu-path-tracing_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cuh", ".cu")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:12]
+
+
+def parity_across_ranks(pkg, dist, torch, rank, world, local, transport):
+    """N-rank correctness inside the bench (the driver's GPU tests run on a 1-GPU box): a small frame through the N
+    ranks of this job must equal the same frame traced by rank 0 alone to 1e-5, every slot must hold exactly its samples."""
+    from cpu_path_tracing_b200.distributed import DistributedRenderer
+
+    W, H, S, seed = 160, 90, 11, 5
+    flags = pkg.PRECISION_FP32 | pkg.VARIANT_MEGAKERNEL_SORTED
+    sph, cfg = pkg.builtin_scene("box_mirror", W, H)
+    cam = pkg.camera_with_config(cfg)
+    dr = DistributedRenderer(pkg, local, rank, world, transport)
+    dr.setup(sph, cam, W, H, 2)
+    r = dr.renderer
+    r.clear()
+    r.render(seed, 0, S, flags)
+    img = r.resolve() if rank == 0 else r.resolve_collective()
+    own = r.download_accum()
+    first, count = pkg.sample_share(S, world, rank)
+    ok = bool(np.all(own[:, 3] == count))
+    total = torch.tensor([float(count), float(r.stats().paths)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    ok = ok and int(total[0].item()) == S and int(total[1].item()) == W * H * 4 * S
+    info = r.comm_info()
+    dr.close()
+    flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank != 0:
+        return None
+    with pkg.Renderer(local) as one:
+        one.upload_scene(sph)
+        one.set_camera(cam)
+        one.set_image(W, H, 2)
+        one.render(seed, 0, S, flags)
+        ref = one.resolve()
+    err = float(np.abs(img - ref).max())
+    good = flag.item() == 1.0 and err < 1e-5
+    return {"status": "ok" if good else "FAILED", "max_abs_image_diff_vs_1_gpu": err, "ranks": world,
+            "slots_hold_their_share": bool(flag.item() == 1.0), "transport": info["last_transport"],
+            "frame": f"box_mirror {W}x{H}, {S} samples per sub-pixel"}
 
 
 if __name__ == "__main__":

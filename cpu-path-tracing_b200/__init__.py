@@ -50,6 +50,22 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} is missing: build it with `make -C {HERE}` (or __graft_entry__.build()). "
         "There is no CPU fallback.")
 
+# The multi-GPU entry points load libnccl.so.2 at run time.  In a Python process that may also import torch, it has to be
+# the SAME file torch's libtorch_cuda.so is linked against (the pip package nvidia-nccl), not an older system copy: the
+# dynamic loader keeps one object per soname, and torch fails to import over a libnccl that lacks its newer symbols.
+if "PTB_NCCL_LIB" not in os.environ:
+    try:
+        import importlib.util as _ilu
+
+        _spec = _ilu.find_spec("nvidia.nccl")
+        for _d in (_spec.submodule_search_locations if _spec is not None else []):
+            _cand = os.path.join(_d, "lib", "libnccl.so.2")
+            if os.path.exists(_cand):
+                os.environ["PTB_NCCL_LIB"] = _cand
+                break
+    except (ImportError, ValueError, AttributeError):
+        pass
+
 _lib = ctypes.CDLL(LIB_PATH)
 
 _vp = ctypes.c_void_p
@@ -68,6 +84,7 @@ class _Stats(ctypes.Structure):
     _fields_ = [
         ("paths", _u64), ("rays", _u64), ("last_render_ms", ctypes.c_double), ("total_render_ms", ctypes.c_double),
         ("kernel_launches", _u64), ("hits_diffuse", _u64), ("hits_specular", _u64), ("hits_dielectric", _u64),
+        ("last_resolve_ms", ctypes.c_double),
     ]
 
 
@@ -81,6 +98,7 @@ class Stats:
     hits_diffuse: int
     hits_specular: int
     hits_dielectric: int
+    last_resolve_ms: float = 0.0
 
 
 def _sig(name, restype, *argtypes):
@@ -124,6 +142,20 @@ _ptb_builtin_scene = _sig("ptb_builtin_scene", ctypes.c_int, ctypes.c_char_p, ct
 _ptb_write_ppm = _sig("ptb_write_ppm", ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.c_int)
 _ptb_write_ppm_smallpt = _sig("ptb_write_ppm_smallpt", ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.c_int)
 _ptb_builtin_smallpt_scene = _sig("ptb_builtin_smallpt_scene", ctypes.c_int, _vp, _sz, ctypes.POINTER(_sz), _vp)
+_ptb_upload_accum = _sig("ptb_upload_accum", ctypes.c_int, _vp, _vp, _sz)
+_ptb_download_accum64 = _sig("ptb_download_accum64", ctypes.c_int, _vp, _vp, _sz)
+_ptb_upload_accum64 = _sig("ptb_upload_accum64", ctypes.c_int, _vp, _vp, _sz)
+_ptb_write_ppm_rgb8 = _sig("ptb_write_ppm_rgb8", ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+_ptb_create_multi = _sig("ptb_create_multi", ctypes.c_int, _vp, ctypes.c_int, ctypes.POINTER(_vp))
+_ptb_comm_unique_id = _sig("ptb_comm_unique_id", ctypes.c_int, _vp)
+_ptb_comm_init_rank = _sig("ptb_comm_init_rank", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int)
+_ptb_comm_set_transport = _sig("ptb_comm_set_transport", ctypes.c_int, _vp, ctypes.c_int)
+_ptb_comm_info = _sig("ptb_comm_info", ctypes.c_int, _vp, _vp)
+_ptb_sample_share = _sig("ptb_sample_share", ctypes.c_int, _u32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_u32),
+                         ctypes.POINTER(_u32))
+
+TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_PEER = 0, 1, 2
+COMM_ID_BYTES = 128
 
 # every symbol include/ptb200.h declares (tests check the header against this list and the .so)
 EXPORTED_SYMBOLS = (
@@ -133,6 +165,9 @@ EXPORTED_SYMBOLS = (
     "ptb_get_stats", "ptb_scene_layout", "ptb_trace_samples", "ptb_rng_draws", "ptb_camera_with_config", "ptb_builtin_scene",
     "ptb_write_ppm", "ptb_write_ppm_smallpt", "ptb_builtin_smallpt_scene", "ptb_set_smallpt_camera",
     "ptb_jit_info", "ptb_jit_last_error",
+    "ptb_upload_accum", "ptb_download_accum64", "ptb_upload_accum64", "ptb_write_ppm_rgb8",
+    "ptb_create_multi", "ptb_comm_unique_id", "ptb_comm_init_rank", "ptb_comm_set_transport", "ptb_comm_info",
+    "ptb_sample_share",
 )
 
 
@@ -213,17 +248,51 @@ def write_ppm(path: str, rgb: np.ndarray, smallpt: bool = False) -> None:
         raise PtbError(rc, f"ptb_write_ppm({path})")
 
 
+def write_ppm_rgb8(path: str, rgb8: np.ndarray, binary: bool = True) -> None:
+    """The 8-bit image of Renderer.resolve_rgb8 as "P6" (binary) or the reference's "P3" token layout."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, c = rgb8.shape
+    assert c == 3
+    rc = _ptb_write_ppm_rgb8(os.fsencode(path), _ptr(rgb8), w, h, 1 if binary else 0)
+    if rc != 0:
+        raise PtbError(rc, f"ptb_write_ppm_rgb8({path})")
+
+
+def sample_share(total: int, n_ranks: int, rank: int) -> tuple[int, int]:
+    """(first, count): the contiguous share of `total` samples that member `rank` of `n_ranks` traces."""
+    first, count = _u32(0), _u32(0)
+    rc = _ptb_sample_share(total, n_ranks, rank, ctypes.byref(first), ctypes.byref(count))
+    if rc != 0:
+        raise PtbError(rc, "ptb_sample_share: bad (total, n_ranks, rank)")
+    return first.value, count.value
+
+
+def comm_unique_id() -> bytes:
+    """128 opaque bytes made on rank 0 of a one-process-per-GPU job; the launcher's side channel carries them."""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    rc = _ptb_comm_unique_id(buf)
+    if rc != 0:
+        raise PtbError(rc, "ptb_comm_unique_id: libnccl.so.2 could not be loaded")
+    return buf.raw
+
+
 # ---- the GPU renderer ------------------------------------------------------------------------------
 class Renderer:
     """One context = one GPU.  Thin, 1:1 over the C ABI."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: a GPU index, or a list of them -- then ONE context spans those GPUs (ptb_create_multi): every call
+        below applies to all of them, render() splits the samples, resolve*() sum across the GPUs."""
         self._ctx = _vp(None)
-        rc = _ptb_create(device, ctypes.byref(self._ctx))
+        if isinstance(device, (list, tuple)):
+            devs = (ctypes.c_int * len(device))(*device)
+            rc = _ptb_create_multi(devs, len(device), ctypes.byref(self._ctx))
+        else:
+            rc = _ptb_create(device, ctypes.byref(self._ctx))
         if rc != 0:
             msg = _ptb_last_error(None).decode()
             self._ctx = _vp(None)
-            raise PtbError(rc, msg)
+            raise PtbError(rc, msg or "bad device list")
         self.device = device
         self.width = self.height = self.nsub = 0
 
@@ -299,6 +368,10 @@ class Renderer:
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.height * self.width * 3
         self._check(_ptb_resolve(self._ctx, _ptr(out)))
 
+    def resolve_rgb8_into(self, out: np.ndarray):
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self.height * self.width * 3
+        self._check(_ptb_resolve_rgb8(self._ctx, _ptr(out)))
+
     def resolve_rgb8(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), dtype=np.uint8)
         self._check(_ptb_resolve_rgb8(self._ctx, _ptr(out)))
@@ -329,6 +402,42 @@ class Renderer:
         out = np.empty((self.height * self.width * self.nsub * self.nsub, 4), dtype=np.float32)
         self._check(_ptb_download_accum(self._ctx, _ptr(out), out.size))
         return out
+
+    def upload_accum(self, accum: np.ndarray):
+        """Restore a checkpoint made by download_accum (same image geometry); continue with render(seed, first = samples held)."""
+        accum = np.ascontiguousarray(accum, dtype=np.float32)
+        self._check(_ptb_upload_accum(self._ctx, _ptr(accum), accum.size))
+
+    def download_accum64(self) -> np.ndarray:
+        out = np.empty((self.height * self.width * self.nsub * self.nsub, 4), dtype=np.float64)
+        self._check(_ptb_download_accum64(self._ctx, _ptr(out), out.size))
+        return out
+
+    def upload_accum64(self, accum: np.ndarray):
+        accum = np.ascontiguousarray(accum, dtype=np.float64)
+        self._check(_ptb_upload_accum64(self._ctx, _ptr(accum), accum.size))
+
+    # -- several GPUs (one process per GPU: comm_init_rank; one process for all: Renderer([0, 1, ...]))
+    def comm_init_rank(self, unique_id: bytes, n_ranks: int, rank: int):
+        """Join a job of n_ranks processes (collective).  Afterwards render() traces this rank's share of the samples and
+        resolve*() are collective: rank 0 receives the image."""
+        assert len(unique_id) == COMM_ID_BYTES
+        self._check(_ptb_comm_init_rank(self._ctx, ctypes.create_string_buffer(unique_id, COMM_ID_BYTES), n_ranks, rank))
+
+    def comm_set_transport(self, transport: int):
+        self._check(_ptb_comm_set_transport(self._ctx, transport))
+
+    def comm_info(self) -> dict:
+        out = np.zeros(6, dtype=np.int32)
+        self._check(_ptb_comm_info(self._ctx, _ptr(out)))
+        d = dict(zip(("n_gpus", "rank", "last_transport", "peer_mapped", "nccl_version", "mode"), [int(v) for v in out]))
+        d["last_transport"] = {0: "none", 1: "nccl", 2: "peer"}[d["last_transport"]]
+        d["mode"] = {0: "single", 1: "one process", 2: "process per GPU"}[d["mode"]]
+        return d
+
+    def resolve_collective(self):
+        """resolve() for ranks other than 0 of a one-process-per-GPU job: takes part, receives nothing."""
+        self._check(_ptb_resolve(self._ctx, None))
 
     # -- introspection
     def stats(self) -> Stats:

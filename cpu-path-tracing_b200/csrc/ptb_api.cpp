@@ -6,8 +6,7 @@
 // live context, and ptb_create fails when no CUDA device is usable.
 #include "../../include/ptb200.h"
 #include "ptb_bvh.hpp"
-#include "ptb_jit.hpp"
-#include "ptb_kernels.h"
+#include "ptb_context.hpp"
 #include "ptb_rng.cuh"
 
 #include <algorithm>
@@ -31,66 +30,6 @@ static std::mutex& device_render_mutex(int device)
 
 using namespace ptb;
 
-struct ptb_context
-{
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr; // the one in use (own or caller's)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-
-    // scene
-    int n = 0;
-    bool have_scene = false, have_camera = false;
-    std::vector<RawSphere> h_spheres;
-    RawCamera h_camera{};
-    RawSphere* d_spheres = nullptr;
-    size_t d_spheres_cap = 0;
-    RawCamera* d_camera = nullptr;
-    double sb_cam8[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // smallpt camera: position, direction, fov factor, push
-    bool have_sbcam = false;
-    double* d_sbcam8 = nullptr;
-    ConstSceneF32 cs{};
-    CameraPair cams{}; // both cameras in the shifted FP32 frame: a kernel argument, not part of the constant block
-    double shift[3] = { 0, 0, 0 };
-    SceneCounts counts{};
-    SmallGeo* d_small = nullptr;
-    BigGeo* d_big = nullptr;
-    int* d_order = nullptr;
-    float4* d_shade = nullptr; // 4 planes of n
-    size_t geo_cap = 0;
-    // bounding-volume hierarchy over the small spheres (ptb_bvh.hpp); built when they do not fit the constant lists
-    float4* d_bvh_nodes = nullptr;
-    SmallGeo* d_bvh_geo = nullptr;
-    int* d_bvh_pos = nullptr;
-    size_t bvh_node_cap = 0, bvh_leaf_cap = 0;
-    int bvh_root = 0;
-    bool have_bvh = false;
-    int bvh_depth = 0, bvh_node_count = 0;
-
-    // image
-    int width = 0, height = 0, ns = 0;
-    size_t nslots = 0;
-    float4* d_accum = nullptr; // owned
-    size_t d_accum_bytes = 0;
-    float4* ext_accum = nullptr; // caller-owned
-    size_t ext_accum_bytes = 0;
-    double* d_accum64 = nullptr;
-    bool accum64_used = false;
-    double* d_rgb = nullptr;
-    uint8_t* d_rgb8 = nullptr;
-
-    DeviceCounters* d_counters = nullptr;
-    // material scattered in place by the sorted megakernel (0 diffuse, 1 specular): a guess from the geometry at
-    // upload, then whichever of the two the previous sorted launch hit more often
-    int inline_material = 1;
-    unsigned long long seen_diffuse = 0, seen_specular = 0; // counter values already accounted for
-    JitCache jit;                 // run-time compiled, scene-specialised sorted megakernels (ptb_jit.hpp)
-    bool last_launch_jit = false;
-    WavefrontBuffers wf{ nullptr, nullptr, nullptr, 0 };
-    ptb_stats stats{};
-};
 
 namespace {
 
@@ -659,6 +598,29 @@ int require_ready(ptb_context* ctx, bool need_image, bool smallpt = false, bool 
 
 } // namespace
 
+namespace ptb {
+float4* api_active_accum(ptb_context* ctx)
+{
+    return active_accum(ctx);
+}
+int api_fail(ptb_context* ctx, int code, char const* what)
+{
+    return fail(ctx, code, what);
+}
+int api_fail_cuda(ptb_context* ctx, cudaError_t e, char const* what)
+{
+    return fail_cuda(ctx, e, what);
+}
+} // namespace ptb
+
+// A handle made by ptb_create_multi stands for several member contexts: the call is theirs (ptb_multi.cpp)
+#define PTB_GROUP(ctx, call) \
+    do { \
+        if((ctx) != nullptr && (ctx)->group != nullptr) { \
+            return (call); \
+        } \
+    } while(0)
+
 extern "C" {
 
 int ptb_device_count(void)
@@ -732,7 +694,13 @@ void ptb_destroy(ptb_context* ctx)
     if(ctx == nullptr) {
         return;
     }
+    if(ctx->group != nullptr) {
+        multi_destroy(ctx);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
+    comm_destroy(ctx); // collective when the context is a rank of a job: peers unmap before anything is freed
     if(ctx->own_stream != nullptr) {
         cudaStreamSynchronize(ctx->own_stream);
     }
@@ -771,6 +739,9 @@ int ptb_set_stream(ptb_context* ctx, void* cuda_stream)
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    if(ctx->group != nullptr) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_stream: a multi-GPU context runs on its members' private streams");
+    }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = static_cast<cudaStream_t>(cuda_stream); // nullptr == the legacy default stream
@@ -781,6 +752,9 @@ int ptb_reset_stream(ptb_context* ctx)
 {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
+    }
+    if(ctx->group != nullptr) {
+        return PTB_OK;
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -793,6 +767,7 @@ int ptb_synchronize(ptb_context* ctx)
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_synchronize(ctx));
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PTB_OK;
@@ -803,6 +778,7 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_upload_scene(ctx, spheres, count, stride));
     // count == 0 is a scene: every ray misses and sees the sky (main.cpp:114-120), spheres may then be null
     if((spheres == nullptr && count != 0) || stride < PTB_SPHERE_BYTES || count > (1u << 24)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need spheres of stride >= 88 bytes (at most 2^24)");
@@ -865,6 +841,7 @@ int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_set_camera(ctx, camera, bytes));
     if(camera == nullptr || bytes != PTB_CAMERA_BYTES) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_camera: need a 176-byte pt::camera");
     }
@@ -893,6 +870,7 @@ int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8)
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_set_smallpt_camera(ctx, cam8));
     bool finite8 = cam8 != nullptr;
     for(int i = 0; finite8 && i < 8; ++i) {
         finite8 = std::isfinite(cam8[i]);
@@ -925,8 +903,17 @@ int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
            (1ull << 31)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_image: bad geometry (need 1 <= num_subpixels <= 8 and < 2^31 sub-pixels)");
     }
+    PTB_GROUP(ctx, multi_set_image(ctx, width, height, num_subpixels));
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if(ctx->comm != nullptr) {
+        // one process per GPU: other ranks may hold mappings of the buffers about to be freed (collective)
+        int const rc = comm_release_peers(ctx);
+        if(rc != PTB_OK) {
+            return rc;
+        }
+    }
+    ctx->buffers_epoch++;
     ctx->width = width;
     ctx->height = height;
     ctx->ns = num_subpixels;
@@ -968,6 +955,7 @@ int ptb_clear(ptb_context* ctx)
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_clear(ctx));
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     if(active_accum(ctx) != nullptr && ctx->nslots > 0) {
         PTB_CUDA(ctx, cudaMemsetAsync(active_accum(ctx), 0, ctx->nslots * sizeof(float4), ctx->stream));
@@ -1003,6 +991,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: unknown flags");
     }
     bool const smallpt = integrator == PTB_INTEGRATOR_SMALLPT;
+    PTB_GROUP(ctx, multi_render(ctx, seed, first_sample, samples_per_subpixel, flags));
     int rc = require_ready(ctx, true, smallpt);
     if(rc != PTB_OK) {
         return rc;
@@ -1017,6 +1006,24 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_render: sample range overflows 32 bits");
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if(ctx->comm != nullptr) {
+        // one process per GPU: this rank traces its share of the range (ptb_sample_share); the rest is the same call
+        uint32_t first = 0, count = 0;
+        int32_t info[6];
+        ptb_comm_info(ctx, info);
+        ptb_sample_share(samples_per_subpixel, info[0], info[1], &first, &count);
+        first_sample += first;
+        samples_per_subpixel = count;
+    }
+    if(precision == PTB_PRECISION_FP64 && ctx->d_accum64 == nullptr) {
+        // (before the early return: with several GPUs a member whose share is empty still takes part in the sum)
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_accum64, ctx->nslots * 4 * sizeof(double)));
+        PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum64, 0, ctx->nslots * 4 * sizeof(double), ctx->stream));
+        ctx->buffers_epoch++;
+    }
+    if(precision == PTB_PRECISION_FP64) {
+        ctx->accum64_used = true;
+    }
     if(samples_per_subpixel == 0) {
         ctx->stats.last_render_ms = 0.0;
         return PTB_OK; // the reference renders a black image for spp < 4 (main.cpp:206)
@@ -1065,11 +1072,6 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     }
     PTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     if(precision == PTB_PRECISION_FP64) {
-        if(ctx->d_accum64 == nullptr) {
-            PTB_CUDA(ctx, cudaMalloc(&ctx->d_accum64, ctx->nslots * 4 * sizeof(double)));
-            PTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum64, 0, ctx->nslots * 4 * sizeof(double), st));
-        }
-        ctx->accum64_used = true;
         if(smallpt) {
             PTB_CUDA(ctx, launch_smallpt_render_f64(key, first_sample, samples_per_subpixel, static_cast<uint32_t>(ctx->width),
                                                     static_cast<uint32_t>(ctx->height), ctx->d_spheres, ctx->n, ctx->d_sbcam8,
@@ -1176,6 +1178,13 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
 
 static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
 {
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_GROUP(ctx, multi_resolve(ctx, rgb_out, rgb8_out, nullptr));
+    if(ctx->comm != nullptr) {
+        return comm_resolve(ctx, rgb_out, rgb8_out, nullptr);
+    }
     int rc = require_ready(ctx, true, false, true);
     if(rc != PTB_OK) {
         return rc;
@@ -1186,10 +1195,12 @@ static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t const st = ctx->stream;
     size_t const npix = static_cast<size_t>(ctx->width) * static_cast<size_t>(ctx->height);
+    PTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     PTB_CUDA(ctx, launch_resolve(active_accum(ctx), ctx->accum64_used ? ctx->d_accum64 : nullptr,
                                  static_cast<uint32_t>(ctx->width), static_cast<uint32_t>(ctx->height),
                                  static_cast<uint32_t>(ctx->ns), rgb_out != nullptr ? ctx->d_rgb : nullptr,
                                  rgb8_out != nullptr ? ctx->d_rgb8 : nullptr, st));
+    PTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += 1;
     if(rgb_out != nullptr) {
         PTB_CUDA(ctx, cudaMemcpyAsync(rgb_out, ctx->d_rgb, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1198,6 +1209,9 @@ static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
         PTB_CUDA(ctx, cudaMemcpyAsync(rgb8_out, ctx->d_rgb8, npix * 3, cudaMemcpyDeviceToHost, st));
     }
     PTB_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.0f;
+    PTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.last_resolve_ms = ms;
     return PTB_OK;
 }
 
@@ -1213,6 +1227,15 @@ int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out)
 
 int ptb_resolve_device(ptb_context* ctx, void** device_rgb)
 {
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    if(ctx->group != nullptr || ctx->comm != nullptr) {
+        if(device_rgb == nullptr) {
+            return fail(ctx, PTB_ERR_ARGUMENT, "ptb_resolve_device: output pointer is null");
+        }
+        return ctx->group != nullptr ? multi_resolve(ctx, nullptr, nullptr, device_rgb) : comm_resolve(ctx, nullptr, nullptr, device_rgb);
+    }
     int rc = require_ready(ctx, true, false, true);
     if(rc != PTB_OK) {
         return rc;
@@ -1235,6 +1258,7 @@ int ptb_measure_fp32_peak(ptb_context* ctx, double* tflops_out)
     if(ctx == nullptr || tflops_out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, ptb_measure_fp32_peak(multi_root(ctx), tflops_out));
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     float* scratch = nullptr;
     PTB_CUDA(ctx, cudaMalloc(&scratch, sizeof(float)));
@@ -1275,6 +1299,9 @@ int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes)
     if(ctx == nullptr || device_ptr == nullptr || bytes == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    if(ctx->group != nullptr) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_accum_buffer: a multi-GPU context holds one buffer per GPU and sums them itself");
+    }
     if(active_accum(ctx) == nullptr) {
         return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
     }
@@ -1287,6 +1314,9 @@ int ptb_set_accum_buffer(ptb_context* ctx, void* device_ptr, size_t bytes)
 {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
+    }
+    if(ctx->group != nullptr) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_set_accum_buffer: a multi-GPU context holds one buffer per GPU and sums them itself");
     }
     if(device_ptr == nullptr) {
         ctx->ext_accum = nullptr;
@@ -1309,6 +1339,7 @@ int ptb_download_accum(ptb_context* ctx, float* out, size_t floats)
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_download_accum(ctx, out, floats));
     if(active_accum(ctx) == nullptr) {
         return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
     }
@@ -1321,11 +1352,76 @@ int ptb_download_accum(ptb_context* ctx, float* out, size_t floats)
     return PTB_OK;
 }
 
+// ---- checkpoint / resume (include/ptb200.h; the reference's TODO, README.md:9) -------------------------------------
+int ptb_upload_accum(ptb_context* ctx, float const* in, size_t floats)
+{
+    if(ctx == nullptr || in == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_GROUP(ctx, multi_upload_accum(ctx, in, floats));
+    if(active_accum(ctx) == nullptr) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(floats != ctx->nslots * 4) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_accum: need exactly width*height*ns*ns*4 floats (a checkpoint of the same image geometry)");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaMemcpyAsync(active_accum(ctx), in, ctx->nslots * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_download_accum64(ptb_context* ctx, double* out, size_t doubles)
+{
+    if(ctx == nullptr || out == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_GROUP(ctx, multi_download_accum64(ctx, out, doubles));
+    if(ctx->width <= 0) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(doubles < ctx->nslots * 4) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_download_accum64: output too small");
+    }
+    if(ctx->d_accum64 == nullptr) { // no FP64 render since ptb_set_image: the buffer is all zeros
+        std::memset(out, 0, ctx->nslots * 4 * sizeof(double));
+        return PTB_OK;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PTB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_accum64, ctx->nslots * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PTB_OK;
+}
+
+int ptb_upload_accum64(ptb_context* ctx, double const* in, size_t doubles)
+{
+    if(ctx == nullptr || in == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_GROUP(ctx, multi_upload_accum64(ctx, in, doubles));
+    if(ctx->width <= 0) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(doubles != ctx->nslots * 4) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_accum64: need exactly width*height*ns*ns*4 doubles");
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if(ctx->d_accum64 == nullptr) {
+        PTB_CUDA(ctx, cudaMalloc(&ctx->d_accum64, ctx->nslots * 4 * sizeof(double)));
+        ctx->buffers_epoch++;
+    }
+    PTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_accum64, in, ctx->nslots * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->accum64_used = true;
+    return PTB_OK;
+}
+
 int ptb_get_stats(ptb_context* ctx, ptb_stats* out)
 {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, multi_get_stats(ctx, out));
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     DeviceCounters c{};
     PTB_CUDA(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1343,6 +1439,7 @@ int ptb_scene_layout(ptb_context* ctx, int32_t out[10])
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, ptb_scene_layout(multi_root(ctx), out));
     if(!ctx->have_scene) {
         return fail(ctx, PTB_ERR_STATE, "no scene: call ptb_upload_scene first");
     }
@@ -1359,6 +1456,7 @@ int ptb_jit_info(ptb_context* ctx, int32_t out[5])
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, ptb_jit_info(multi_root(ctx), out));
     out[0] = ctx->jit.available() ? 1 : 0;
     out[1] = ctx->jit.compiled();
     out[2] = ctx->jit.failures();
@@ -1369,6 +1467,9 @@ int ptb_jit_info(ptb_context* ctx, int32_t out[5])
 
 char const* ptb_jit_last_error(ptb_context* ctx)
 {
+    if(ctx != nullptr && ctx->group != nullptr) {
+        return ptb_jit_last_error(multi_root(ctx));
+    }
     return ctx != nullptr ? ctx->jit.last_error().c_str() : "";
 }
 
@@ -1378,6 +1479,14 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
 {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
+    }
+    if(ctx->group != nullptr) { // the parity probe needs one GPU: the root's
+        int const rc_ = ptb_trace_samples(multi_root(ctx), seed, x, y, sx, sy, sample, count, flags, primary_hit_out, radiance_out,
+                                          ray_out, draws_out);
+        if(rc_ != PTB_OK) {
+            ctx->err = multi_root(ctx)->err;
+        }
+        return rc_;
     }
     bool const smallpt = (flags & PTB_INTEGRATOR_MASK) == PTB_INTEGRATOR_SMALLPT;
     int rc = require_ready(ctx, false, smallpt);
@@ -1500,6 +1609,7 @@ int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
+    PTB_GROUP(ctx, ptb_rng_draws(multi_root(ctx), seed, slot, sample, count, n_draws, draws_out));
     if(slot == nullptr || sample == nullptr || draws_out == nullptr || n_draws <= 0 || count == 0 || count > (1u << 28)) {
         return fail(ctx, PTB_ERR_ARGUMENT, "ptb_rng_draws: bad arguments");
     }

@@ -310,7 +310,10 @@ __global__ void render_f64_kernel(uint64_t key, uint32_t first_sample, uint32_t 
         uint32_t const pix = q / ns;
         uint32_t const y = pix / width;
         uint32_t const x = pix - y * width;
-        V3 sum = mk(0, 0, 0);
+        // the running sum CONTINUES from what the slot holds (main.cpp:184-191 adds sample after sample): a render split
+        // into several calls, or resumed from a checkpoint, performs the very same additions as one call
+        double* a = accum + 4 * static_cast<size_t>(slot);
+        V3 sum = mk(a[0], a[1], a[2]);
         for(uint32_t s = 0; s < samples; ++s) {
             Rng64 rng;
             rng.g = rng_open(key, slot, first_sample + s);
@@ -318,10 +321,9 @@ __global__ void render_f64_kernel(uint64_t key, uint32_t first_sample, uint32_t 
             Ray64 const pr = primary_ray(cam, x, y, sx, sy, width, height, ns, rng);
             sum = sum + radiance(sph, n, pr, rng, cnt);
         }
-        double* a = accum + 4 * static_cast<size_t>(slot);
-        a[0] += sum.x;
-        a[1] += sum.y;
-        a[2] += sum.z;
+        a[0] = sum.x;
+        a[1] = sum.y;
+        a[2] = sum.z;
         a[3] += static_cast<double>(samples);
     }
     uint32_t const rays = __reduce_add_sync(0xffffffffu, cnt.rays);

@@ -119,6 +119,42 @@ int ptb_write_ppm_smallpt(char const* path, double const* rgb, int width, int he
     return write_ppm_with(path, rgb, width, height, [](double v) { return pt::smallpt_to_int(v); });
 }
 
+// The 8-bit values of ptb_resolve_rgb8 (pt::color_to_int on the GPU) to disk: raw "P6", or the reference's "P3"
+// token layout (main.cpp:240-247) through a table of the 256 possible tokens -- no pow(), no integer formatting.
+int ptb_write_ppm_rgb8(char const* path, uint8_t const* rgb8, int width, int height, int binary)
+{
+    if(path == nullptr || rgb8 == nullptr || width <= 0 || height <= 0) {
+        return PTB_ERR_ARGUMENT;
+    }
+    std::FILE* f = std::fopen(path, "wb");
+    if(f == nullptr) {
+        return PTB_ERR_IO;
+    }
+    size_t const n = static_cast<size_t>(width) * static_cast<size_t>(height) * 3;
+    std::string const head = std::string(binary != 0 ? "P6\n" : "P3\n") + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
+    bool ok = std::fwrite(head.data(), 1, head.size(), f) == head.size();
+    if(binary != 0) {
+        ok = ok && std::fwrite(rgb8, 1, n, f) == n;
+    }
+    else {
+        char token[256][4];
+        unsigned char len[256];
+        for(int v = 0; v < 256; ++v) {
+            len[v] = static_cast<unsigned char>(std::snprintf(token[v], 4, "%d", v));
+            token[v][len[v]++] = ' '; // "{v} ": at most four bytes, no terminator kept
+        }
+        std::vector<char> buf(n * 4);
+        size_t m = 0;
+        for(size_t i = 0; i < n; ++i) {
+            unsigned const v = rgb8[i];
+            std::memcpy(&buf[m], token[v], 4);
+            m += len[v];
+        }
+        ok = ok && std::fwrite(buf.data(), 1, m, f) == m;
+    }
+    return (std::fclose(f) == 0 && ok) ? PTB_OK : PTB_ERR_IO;
+}
+
 // Same bytes as the writer of /root/reference/src/main.cpp:240-247: header
 // "P3\n{w} {h}\n255\n", then "{r} {g} {b} " per pixel, no newlines.
 int ptb_write_ppm(char const* path, double const* rgb, int width, int height)

@@ -126,6 +126,17 @@ cudaError_t launch_render_f64(uint64_t key, uint32_t first_sample, uint32_t samp
 // accum32: float4 per slot; accum64: 4 doubles per slot (either may be null, both are summed when present)
 cudaError_t launch_resolve(float4 const* accum32, double const* accum64, uint32_t width, uint32_t height, uint32_t ns,
                            double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream);
+// The same kernel over the buffers of SEVERAL GPUs (peer mappings) and a range of pixel rows [y0, y1) in the reference's
+// row numbering (before the flip): G such launches, one per GPU, sum + resolve + gather the image (ptb_multi.cpp).
+constexpr int kMaxGpus = 16;
+struct ResolveSources
+{
+    float4 const* accum32[kMaxGpus];
+    double const* accum64[kMaxGpus];
+    int n;
+};
+cudaError_t launch_resolve_rows(ResolveSources const& src, uint32_t width, uint32_t height, uint32_t ns, uint32_t y0,
+                                uint32_t y1, double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream);
 
 // ---- FP32 peak calibration (FFMA loop) ------------------------------------------------------------------------
 cudaError_t launch_fp32_peak(int sm_count, int iters, float* scratch, cudaStream_t stream, double* flop_out);

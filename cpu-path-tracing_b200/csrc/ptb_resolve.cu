@@ -17,41 +17,75 @@ __device__ __forceinline__ double clamp01(double v)
     return v < 0.0 ? 0.0 : (1.0 < v ? 1.0 : v);
 }
 
-__global__ void resolve_kernel(float4 const* __restrict__ accum32, double const* __restrict__ accum64, uint32_t width,
-                               uint32_t height, uint32_t ns, double* __restrict__ rgb_out, uint8_t* __restrict__ rgb8_out)
+// One kernel for one GPU and for many.  `src` lists the accumulation buffers of ALL GPUs of the job (FP32 float4 sums
+// and / or FP64 sums, per slot); on another GPU they are peer mappings (NVLink), as is `rgb_out` / `rgb8_out` when
+// this GPU is not the one that owns the image.  The launch covers the pixel rows [y0, y1) -- this GPU's share -- so with
+// G GPUs the G launches together are reduce-scatter + resolve + gather of the image in one pass over the data: every
+// slot is read once from every buffer, nothing but pixels is written.
+//
+// Threads map to SLOTS for the loads (a warp reads 512 contiguous bytes of each buffer -- full lines over NVLink),
+// the per-slot clamped means go through shared memory, then one thread per pixel adds its ns*ns strata in the
+// reference's order (sy outer, sx inner: main.cpp:223-227).  Double arithmetic like the reference's.
+constexpr int kResolveThreads = 256;
+
+__global__ void __launch_bounds__(kResolveThreads)
+    resolve_kernel(ResolveSources const src, uint32_t width, uint32_t height, uint32_t ns, uint32_t y0, uint32_t y1,
+                   double* __restrict__ rgb_out, uint8_t* __restrict__ rgb8_out)
 {
-    uint32_t const pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if(pix >= width * height) {
+    __shared__ double s_mean[kResolveThreads * 3];
+    uint32_t const nsub = ns * ns;
+    uint32_t const ppb = kResolveThreads / nsub; // pixels per block (nsub <= 64)
+    uint32_t const pix0 = y0 * width + blockIdx.x * ppb;
+    uint32_t const pix_end = y1 * width;
+    uint32_t const t = threadIdx.x;
+    if(t < ppb * nsub) {
+        uint32_t const pix = pix0 + t / nsub;
+        double sr = 0.0, sg = 0.0, sb = 0.0, n = 0.0;
+        if(pix < pix_end) {
+            size_t const slot = static_cast<size_t>(pix0) * nsub + t;
+            for(int g = 0; g < src.n; ++g) {
+                if(src.accum32[g] != nullptr) {
+                    float4 const a = __ldcv(src.accum32[g] + slot); // another GPU wrote it: never from a stale line
+                    sr += a.x;
+                    sg += a.y;
+                    sb += a.z;
+                    n += a.w;
+                }
+                if(src.accum64[g] != nullptr) {
+                    double2 const lo = __ldcv(reinterpret_cast<double2 const*>(src.accum64[g] + 4 * slot));
+                    double2 const hi = __ldcv(reinterpret_cast<double2 const*>(src.accum64[g] + 4 * slot) + 1);
+                    sr += lo.x;
+                    sg += lo.y;
+                    sb += hi.x;
+                    n += hi.y;
+                }
+            }
+        }
+        double mr = 0.0, mg = 0.0, mb = 0.0;
+        if(n > 0.0) {
+            double const inv = 1.0 / n;
+            mr = clamp01(sr * inv);
+            mg = clamp01(sg * inv);
+            mb = clamp01(sb * inv);
+        }
+        s_mean[3 * t + 0] = mr;
+        s_mean[3 * t + 1] = mg;
+        s_mean[3 * t + 2] = mb;
+    }
+    __syncthreads();
+    uint32_t const pix = pix0 + t;
+    if(t >= ppb || pix >= pix_end) {
         return;
     }
-    uint32_t const y = pix / width;
-    uint32_t const x = pix - y * width;
-    uint32_t const nsub = ns * ns;
     double const w = 1.0 / static_cast<double>(nsub);
     double r = 0.0, g = 0.0, b = 0.0;
     for(uint32_t k = 0; k < nsub; ++k) {
-        size_t const slot = static_cast<size_t>(pix) * nsub + k;
-        double sr = 0.0, sg = 0.0, sb = 0.0, n = 0.0;
-        if(accum32 != nullptr) {
-            float4 const a = accum32[slot];
-            sr += a.x;
-            sg += a.y;
-            sb += a.z;
-            n += a.w;
-        }
-        if(accum64 != nullptr) {
-            sr += accum64[4 * slot + 0];
-            sg += accum64[4 * slot + 1];
-            sb += accum64[4 * slot + 2];
-            n += accum64[4 * slot + 3];
-        }
-        if(n > 0.0) {
-            double const inv = 1.0 / n;
-            r = r + clamp01(sr * inv) * w;
-            g = g + clamp01(sg * inv) * w;
-            b = b + clamp01(sb * inv) * w;
-        }
+        r = r + s_mean[3 * (t * nsub + k) + 0] * w;
+        g = g + s_mean[3 * (t * nsub + k) + 1] * w;
+        b = b + s_mean[3 * (t * nsub + k) + 2] * w;
     }
+    uint32_t const y = pix / width;
+    uint32_t const x = pix - y * width;
     size_t const row = static_cast<size_t>(height - y - 1) * width + x;
     if(rgb_out != nullptr) {
         rgb_out[3 * row + 0] = r;
@@ -96,17 +130,26 @@ cudaError_t launch_fp32_peak(int sm_count, int iters, float* scratch, cudaStream
     return cudaGetLastError();
 }
 
+cudaError_t launch_resolve_rows(ResolveSources const& src, uint32_t width, uint32_t height, uint32_t ns, uint32_t y0,
+                                uint32_t y1, double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream)
+{
+    if(y1 <= y0 || width == 0 || ns == 0 || ns * ns > 64u) {
+        return y1 <= y0 || width == 0 ? cudaSuccess : cudaErrorInvalidValue;
+    }
+    uint32_t const ppb = static_cast<uint32_t>(kResolveThreads) / (ns * ns);
+    uint32_t const npix = (y1 - y0) * width;
+    resolve_kernel<<<(npix + ppb - 1) / ppb, kResolveThreads, 0, stream>>>(src, width, height, ns, y0, y1, rgb_out, rgb8_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(float4 const* accum32, double const* accum64, uint32_t width, uint32_t height, uint32_t ns,
                            double* rgb_out, uint8_t* rgb8_out, cudaStream_t stream)
 {
-    uint32_t const npix = width * height;
-    if(npix == 0) {
-        return cudaSuccess;
-    }
-    unsigned const threads = 256;
-    resolve_kernel<<<(npix + threads - 1) / threads, threads, 0, stream>>>(accum32, accum64, width, height, ns, rgb_out,
-                                                                           rgb8_out);
-    return cudaGetLastError();
+    ResolveSources src{};
+    src.n = 1;
+    src.accum32[0] = accum32;
+    src.accum64[0] = accum64;
+    return launch_resolve_rows(src, width, height, ns, 0, height, rgb_out, rgb8_out, stream);
 }
 
 } // namespace ptb

@@ -320,7 +320,8 @@ __global__ void smallpt_render_f64_kernel(uint64_t key, uint32_t first_sample, u
         Cam64 const cam = make_camera(cam8, width, height);
         uint32_t const sx = slot & 1u, sy = (slot >> 1) & 1u, pix = slot >> 2;
         uint32_t const y = pix / width, x = pix - y * width;
-        V3 sum = mk(0, 0, 0);
+        double* a = accum + 4 * static_cast<size_t>(slot);
+        V3 sum = mk(a[0], a[1], a[2]); // continues the slot's running sum: split or resumed renders add in the same order
         for(uint32_t s = 0; s < samples; ++s) {
             Rng64 rng;
             rng.g = rng_open(key, slot, first_sample + s);
@@ -328,10 +329,9 @@ __global__ void smallpt_render_f64_kernel(uint64_t key, uint32_t first_sample, u
             Ray64 const pr = camera_ray(cam, x, y, sx, sy, width, height, rng);
             sum = sum + radiance(sph, n, pr, rng, cnt);
         }
-        double* a = accum + 4 * static_cast<size_t>(slot);
-        a[0] += sum.x;
-        a[1] += sum.y;
-        a[2] += sum.z;
+        a[0] = sum.x;
+        a[1] = sum.y;
+        a[2] = sum.z;
         a[3] += static_cast<double>(samples);
     }
     uint32_t const rays = __reduce_add_sync(0xffffffffu, cnt.rays);

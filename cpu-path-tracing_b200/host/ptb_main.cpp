@@ -7,12 +7,19 @@
 // replaced: ptb_upload_scene / ptb_set_camera / ptb_set_image / ptb_render / ptb_resolve.
 //
 //   ptb_main [spp] [--scene simple|box|box_mirror|dof_glass|spheres10k] [--size WxH]
-//            [--seed N] [--fp64] [--out image.ppm] [--device N]
-//            [--variant sorted|inplace|wavefront] [--precompiled] [--scan]
+//            [--seed N] [--fp64] [--out image.ppm] [--device N | --devices 0,1,..,7]
+//            [--variant sorted|inplace|wavefront] [--precompiled] [--scan] [--p6 | --rgb8]
+//
+// --devices: ONE process, several GPUs (ptb_create_multi): the samples of every sub-pixel are split over them and summed
+// inside the library -- still one blocking ptb_render + one ptb_resolve, as the reference has one executor.run().wait().
+// --p6 / --rgb8: the output stage for large images: gamma + 8-bit conversion on the GPU (ptb_resolve_rgb8: 3 bytes per
+// pixel come back instead of 24), written as binary "P6" or as the reference's "P3" tokens (main.cpp:240-247).
 #include "../../include/ptb200.h"
 #include "pt.hpp"
 
+#include <algorithm>
 #include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,7 +44,8 @@ auto main(int argc, char* argv[]) -> int
     int width = 1024;
     int height = 768;
     int spp = 4;
-    int device = 0;
+    std::vector<int> devices{ 0 };
+    int output_mode = 0; // 0: FP64 image + the reference's writer, 1: 8-bit image as P6, 2: 8-bit image as P3
     unsigned long long seed = 1;
     unsigned flags = PTB_VARIANT_MEGAKERNEL_SORTED | PTB_PRECISION_FP32;
     std::string scene_name{ "box_mirror" };
@@ -60,7 +68,22 @@ auto main(int argc, char* argv[]) -> int
             seed = std::strtoull(next().c_str(), nullptr, 0);
         }
         else if(a == "--device") {
-            device = std::atoi(next().c_str());
+            devices = { std::atoi(next().c_str()) };
+        }
+        else if(a == "--devices") {
+            devices.clear();
+            std::string const list = next();
+            for(std::size_t pos = 0; pos <= list.size();) {
+                std::size_t const comma = std::min(list.find(',', pos), list.size());
+                devices.push_back(std::atoi(list.substr(pos, comma - pos).c_str()));
+                pos = comma + 1;
+            }
+        }
+        else if(a == "--p6") {
+            output_mode = 1;
+        }
+        else if(a == "--rgb8") {
+            output_mode = 2;
         }
         else if(a == "--out") {
             out = next();
@@ -114,7 +137,7 @@ auto main(int argc, char* argv[]) -> int
     image.resize(static_cast<std::size_t>(width) * static_cast<std::size_t>(height), pt::vec3{ 0, 0, 0 });
 
     ptb_context* ctx = nullptr;
-    int rc = ptb_create(device, &ctx);
+    int rc = devices.size() == 1 ? ptb_create(devices[0], &ctx) : ptb_create_multi(devices.data(), static_cast<int>(devices.size()), &ctx);
     if(rc != PTB_OK) {
         std::cerr << "ptb_create failed (" << rc << "): " << ptb_last_error(nullptr) << '\n';
         return 1;
@@ -130,12 +153,20 @@ auto main(int argc, char* argv[]) -> int
     }
 
     std::cerr << "Rendering (" << samps * num_subpixels * num_subpixels << " spp) " << scene_name << ' ' << width << 'x'
-              << height << " on GPU " << device << '\n';
+              << height << " on " << devices.size() << " GPU(s), first " << devices[0] << '\n';
     auto const t0 = std::chrono::steady_clock::now();
     if((rc = ptb_render(ctx, seed, 0, static_cast<unsigned>(samps), flags)) != PTB_OK) {
         return die(ctx, "ptb_render", rc);
     }
-    if((rc = ptb_resolve(ctx, reinterpret_cast<double*>(image.data()))) != PTB_OK) {
+    std::vector<std::uint8_t> image8{};
+    if(output_mode == 0) {
+        rc = ptb_resolve(ctx, reinterpret_cast<double*>(image.data()));
+    }
+    else {
+        image8.resize(static_cast<std::size_t>(width) * static_cast<std::size_t>(height) * 3);
+        rc = ptb_resolve_rgb8(ctx, image8.data());
+    }
+    if(rc != PTB_OK) {
         return die(ctx, "ptb_resolve", rc);
     }
     auto const t1 = std::chrono::steady_clock::now();
@@ -150,7 +181,17 @@ auto main(int argc, char* argv[]) -> int
               << static_cast<double>(st.paths) / (st.last_render_ms > 0 ? st.last_render_ms : 1) * 1e-3 << " Mpaths/s, "
               << static_cast<double>(st.rays) / (st.last_render_ms > 0 ? st.last_render_ms : 1) * 1e-3 << " Mrays/s\n";
 
-    rc = ptb_write_ppm(out.c_str(), reinterpret_cast<double const*>(image.data()), width, height);
+    int32_t comm[6] = { 1, 0, 0, 0, 0, 0 };
+    ptb_comm_info(ctx, comm);
+    if(comm[0] > 1) {
+        std::cerr << "  " << comm[0] << " GPUs, sum + resolve " << st.last_resolve_ms << " ms over "
+                  << (comm[2] == PTB_TRANSPORT_PEER ? "peer mappings (one fused kernel per GPU)" : "NCCL") << '\n';
+    }
+    auto const w0 = std::chrono::steady_clock::now();
+    rc = output_mode == 0 ? ptb_write_ppm(out.c_str(), reinterpret_cast<double const*>(image.data()), width, height)
+                          : ptb_write_ppm_rgb8(out.c_str(), image8.data(), width, height, output_mode == 1 ? 1 : 0);
+    std::cerr << "  image written in " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count()
+              << " ms\n";
     ptb_destroy(ctx);
     if(rc != PTB_OK) {
         std::cerr << "cannot write " << out << '\n';

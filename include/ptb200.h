@@ -17,8 +17,8 @@
  *
  * Conventions: every call returns 0 on success or a negative ptb_status; nothing
  * throws across the boundary; the caller owns every host buffer it passes; the
- * library owns all device memory behind the opaque context.  A context is bound
- * to ONE GPU and is not thread-safe (one process / one host thread per GPU, as
+ * library owns all device memory behind the opaque context.  A context made by
+ * ptb_create is bound to ONE GPU (ptb_create_multi: to a list of GPUs) and is not thread-safe (one process / one host thread per GPU, as
  * under torchrun); several contexts may be driven from several threads, renders
  * on the same GPU then take turns.  There is NO CPU fallback: without a usable CUDA device
  * ptb_create fails with PTB_ERR_NO_DEVICE.
@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 3
+#define PTB_ABI_VERSION 4
 
 #define PTB_SPHERE_BYTES 88
 #define PTB_CAMERA_BYTES 176
@@ -93,6 +93,7 @@ typedef struct ptb_stats
     uint64_t hits_diffuse;   /* scatter events by material since the last ptb_clear */
     uint64_t hits_specular;
     uint64_t hits_dielectric;
+    double last_resolve_ms;  /* device time of the last ptb_resolve* on this context, cross-GPU summation included */
 } ptb_stats;
 
 /* ---- library ----------------------------------------------------------------- */
@@ -159,10 +160,56 @@ int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out);
  * owned by the context (valid until the next ptb_set_image / ptb_destroy).  No copy. */
 int ptb_resolve_device(ptb_context* ctx, void** device_rgb);
 
-/* ---- multi-GPU plumbing ------------------------------------------------------------- */
-/* Device address and size of the FP32 accumulation buffer, so that the caller's
- * collective layer (torch.distributed / NCCL) can sum it across ranks in place
- * before ptb_resolve on the root.  Slots carry their own sample count in .w, so
+/* ---- several GPUs behind the same calls ---------------------------------------------------------------
+ * The reference fills the whole image with ONE blocking call on ONE machine (src/main.cpp:214-236, a taskflow
+ * task per row).  Here the work is split over GPUs by SAMPLES: member g of G traces the contiguous share
+ * ptb_sample_share(S, G, g) of the samples [first_sample, first_sample + S) of every sub-pixel into its own
+ * accumulation buffer -- the stream is keyed by the absolute sample index, so the image does not depend on G --
+ * and the un-clamped per-stratum sums (and their counts, in .w) are summed across GPUs before the non-linear
+ * resolve (main.cpp:192-196).  Two ways to get there, same entry points afterwards:
+ *
+ *  (1) ptb_create_multi: ONE host process drives n GPUs -- what a patched src/main.cpp uses.
+ *      Every call on the handle applies to all members: ptb_upload_scene / ptb_set_camera / ptb_set_image /
+ *      ptb_clear broadcast, ptb_render runs the members' shares concurrently (one host thread per GPU) and
+ *      blocks until all are done, ptb_resolve* sum + resolve and fill the caller's image.
+ *  (2) ptb_comm_init_rank: ONE process per GPU (torchrun, mpirun).  Rank 0 makes an id with
+ *      ptb_comm_unique_id and hands it to the others by whatever side channel the launcher has; after
+ *      ptb_comm_init_rank every rank makes the same calls: ptb_render traces this rank's share, ptb_resolve* are
+ *      COLLECTIVE (every rank must call; rank 0 receives the image, the others may pass NULL).
+ *
+ * How the sums travel (PTB_TRANSPORT_*): AUTO picks PEER when every GPU can map the others' memory (NVLink /
+ * NVSwitch; CUDA IPC between processes), else NCCL.
+ *   PEER  one kernel per GPU does reduce-scatter + resolve + gather at once: GPU g reads rows [g*H/G, (g+1)*H/G)
+ *         of ALL members' accumulation buffers through peer loads, resolves them and stores the pixels straight into
+ *         the root's image.  Nothing is written but the image; accumulation buffers stay as they are (progressive).
+ *   NCCL  ncclReduce(sum) of the buffers into a scratch buffer on the root (library-owned communicator, libnccl.so.2
+ *         loaded at run time), then the single-GPU resolve there.
+ * ptb_stats.last_resolve_ms is the device time of either, ptb_comm_info says which one ran. */
+int ptb_create_multi(int const* devices, int n_devices, ptb_context** out);
+
+#define PTB_COMM_ID_BYTES 128
+enum
+{
+    PTB_TRANSPORT_AUTO = 0,
+    PTB_TRANSPORT_NCCL = 1,
+    PTB_TRANSPORT_PEER = 2
+};
+/* 128 opaque bytes (an ncclUniqueId) made on rank 0; needs libnccl.so.2 (PTB_ERR_STATE when it cannot be loaded). */
+int ptb_comm_unique_id(void* id_out);
+/* Join a job of n_ranks processes as `rank`; collective (blocks until every rank has called it). */
+int ptb_comm_init_rank(ptb_context* ctx, void const* id, int n_ranks, int rank);
+/* PTB_TRANSPORT_*: a request; PEER falls back to NCCL where peer mapping is impossible.  Must be the same on all ranks. */
+int ptb_comm_set_transport(ptb_context* ctx, int transport);
+/* out = { number of GPUs (1 for a plain context), this context's rank (0 for a ptb_create_multi handle),
+ *         transport of the last resolve (PTB_TRANSPORT_NCCL / _PEER, 0 = none yet), 1 if peer mapping is available,
+ *         NCCL version code (0 = not loaded), 1 for a single-process group / 2 for one process per GPU / 0 }. */
+int ptb_comm_info(ptb_context* ctx, int32_t out[6]);
+/* The share of `total` samples that member `rank` of `n_ranks` traces: contiguous, sizes differ by at most one. */
+int ptb_sample_share(uint32_t total, int n_ranks, int rank, uint32_t* first_out, uint32_t* count_out);
+
+/* ---- caller-side plumbing (single-GPU contexts only) ----------------------------------------------------- */
+/* Device address and size of the FP32 accumulation buffer, for a caller that runs its own collective layer
+ * (e.g. torch.distributed) instead of the calls above.  Slots carry their own sample count in .w, so
  * a plain sum-reduce is all that is needed. */
 int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes);
 /* Render into / resolve from a caller-owned device buffer (e.g. a torch tensor)
@@ -170,6 +217,17 @@ int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes);
 int ptb_set_accum_buffer(ptb_context* ctx, void* device_ptr, size_t bytes);
 /* Host copy of the accumulation buffer (float4 per slot). */
 int ptb_download_accum(ptb_context* ctx, float* out, size_t floats);
+
+/* ---- checkpoint / resume (the reference's own TODO, README.md:9: "save progress to resume") ------ */
+/* ptb_download_accum IS the checkpoint of a progressive FP32 render: un-clamped per-stratum sums and, in .w, how
+ * many samples each slot holds.  ptb_upload_accum restores it into a context whose image geometry matches
+ * (floats == width*height*ns*ns*4): the buffer is REPLACED, and rendering continues with
+ * ptb_render(seed, first_sample = samples already in the checkpoint, ...) -- the stream is keyed by the absolute
+ * sample index, so save -> destroy -> create -> restore -> continue gives the slots an uninterrupted run gives.
+ * The 64-bit pair does the same for PTB_PRECISION_FP64 renders (4 doubles per slot), bit for bit. */
+int ptb_upload_accum(ptb_context* ctx, float const* in, size_t floats);
+int ptb_download_accum64(ptb_context* ctx, double* out, size_t doubles);
+int ptb_upload_accum64(ptb_context* ctx, double const* in, size_t doubles);
 
 /* ---- introspection ------------------------------------------------------------------ */
 int ptb_get_stats(ptb_context* ctx, ptb_stats* out);
@@ -223,6 +281,10 @@ int ptb_builtin_smallpt_scene(void* spheres_out, size_t capacity, size_t* count_
 int ptb_write_ppm(char const* path, double const* rgb, int width, int height);
 /* Same, with the sandbox's rounding: int(pow(clamp(x), 1/2.2) * 255 + .5), sandbox/main.cpp:130-133,271-275. */
 int ptb_write_ppm_smallpt(char const* path, double const* rgb, int width, int height);
+/* The output stage for large images (src/main.cpp:240-247 spends its time in 3*W*H pow() calls and integer
+ * formatting): write the 8-bit values ptb_resolve_rgb8 produced on the GPU.  binary != 0: "P6" (raw bytes, 3*W*H);
+ * binary == 0: the reference's ASCII "P3" layout, token for token, through a 256-entry table. */
+int ptb_write_ppm_rgb8(char const* path, uint8_t const* rgb8, int width, int height, int binary);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,24 @@ def test_write_ppm_matches_reference_format(pkg, oracle_port, tmp_path):
     assert text.endswith(" ") and text.count("\n") == 3  # main.cpp:241-246: one token + space per channel, no line breaks
 
 
+def test_write_ppm_rgb8_p3_is_the_reference_layout_and_p6_is_raw(pkg, oracle_port, tmp_path):
+    """main.cpp:240-247 from 8-bit values (ptb_resolve_rgb8 does color_to_int on the GPU): same bytes as ptb_write_ppm."""
+    rng = np.random.default_rng(5)
+    img = rng.uniform(-0.2, 1.3, size=(11, 13, 3))
+    img[0, 0] = (0.0, 1.0, 0.5)
+    rgb8 = oracle_port.color_to_int(img).astype(np.uint8)
+    a, b, c = (os.path.join(tmp_path, n) for n in ("a.ppm", "b.ppm", "c.ppm"))
+    pkg.write_ppm(a, img)
+    pkg.write_ppm_rgb8(b, rgb8, binary=False)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    pkg.write_ppm_rgb8(c, rgb8, binary=True)
+    raw = open(c, "rb").read()
+    head = b"P6\n13 11\n255\n"
+    assert raw.startswith(head) and raw[len(head):] == rgb8.tobytes()
+    lib = __import__("ctypes").CDLL(pkg.LIB_PATH)
+    assert lib.ptb_write_ppm_rgb8(None, None, 1, 1, 1) == -1
+
+
 def test_refmain_golden_rows_are_the_shipped_scene(golden, golden_scene, oracle_port):
     """The reference PROGRAM's reproducible rows (y%64==0) re-derived by the oracle from mt19937{0}."""
     z = golden("refmain_rows.npz")

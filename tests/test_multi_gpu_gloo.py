@@ -26,6 +26,27 @@ def test_sample_range_partitions(pkg):
             assert max(counts) - min(counts) <= 1
     with pytest.raises(ValueError):
         sample_range(8, 2, 2)
+    # the partition is the LIBRARY's (ptb_sample_share, what ptb_render applies on a rank of a job): host code, no GPU
+    assert pkg.sample_share(1024, 8, 3) == (384, 128) and pkg.sample_share(10, 4, 1) == (3, 3)
+    with pytest.raises(pkg.PtbError):
+        pkg.sample_share(8, 0, 0)
+
+
+def test_multi_gpu_entry_points_without_a_gpu(pkg):
+    """No GPU here: the multi-GPU entry points must refuse, not fall back to anything."""
+    import ctypes
+
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.PtbError) as e:
+        pkg.Renderer([0, 1])
+    assert e.value.code == -2  # PTB_ERR_NO_DEVICE from the first member
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    out = ctypes.c_void_p()
+    devs = (ctypes.c_int * 2)(0, 0)
+    assert lib.ptb_create_multi(devs, 2, ctypes.byref(out)) == -1  # a GPU listed twice
+    assert lib.ptb_create_multi(None, 2, ctypes.byref(out)) == -1
+    assert lib.ptb_comm_init_rank(None, None, 2, 0) == -1
 
 
 def _worker(rank, world, port, out_path):
