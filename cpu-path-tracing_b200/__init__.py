@@ -135,6 +135,7 @@ _ptb_jit_info = _sig("ptb_jit_info", ctypes.c_int, _vp, _vp)
 _ptb_jit_last_error = _sig("ptb_jit_last_error", ctypes.c_char_p, _vp)
 _ptb_trace_samples = _sig("ptb_trace_samples", ctypes.c_int, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp,
                           _vp, _vp)
+_ptb_trace_paths = _sig("ptb_trace_paths", ctypes.c_int, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp)
 _ptb_rng_draws = _sig("ptb_rng_draws", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, ctypes.c_int, _vp)
 _ptb_camera_with_config = _sig("ptb_camera_with_config", ctypes.c_int, _vp, _vp)
 _ptb_builtin_scene = _sig("ptb_builtin_scene", ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _vp, _sz,
@@ -167,7 +168,7 @@ EXPORTED_SYMBOLS = (
     "ptb_jit_info", "ptb_jit_last_error",
     "ptb_upload_accum", "ptb_download_accum64", "ptb_upload_accum64", "ptb_write_ppm_rgb8",
     "ptb_create_multi", "ptb_comm_unique_id", "ptb_comm_init_rank", "ptb_comm_set_transport", "ptb_comm_info",
-    "ptb_sample_share",
+    "ptb_sample_share", "ptb_trace_paths",
 )
 
 
@@ -473,6 +474,14 @@ class Renderer:
         self._check(_ptb_trace_samples(self._ctx, seed, *[_ptr(a) for a in arrs], count, flags, _ptr(hit), _ptr(rad),
                                        _ptr(ray), _ptr(draws)))
         return hit, rad, ray, draws
+
+    def trace_paths(self, seed, xs, ys, sxs, sys_, samples, trail_len=32) -> np.ndarray:
+        """[count, trail_len] sphere index hit at each depth (FP64 mode): -1 sky, -2 path over."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, sxs, sys_, samples)]
+        count = arrs[0].size
+        trail = np.zeros((count, trail_len), dtype=np.int32)
+        self._check(_ptb_trace_paths(self._ctx, seed, *[_ptr(a) for a in arrs], count, trail_len, _ptr(trail)))
+        return trail
 
     def rng_draws(self, seed, slots, samples, n_draws) -> np.ndarray:
         slots = np.ascontiguousarray(slots, dtype=np.uint32)

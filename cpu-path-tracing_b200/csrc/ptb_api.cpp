@@ -1603,6 +1603,67 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
     return PTB_OK;
 }
 
+int ptb_trace_paths(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,
+                    uint32_t const* sy, uint32_t const* sample, size_t count, int trail_len, int32_t* trail_out)
+{
+    if(ctx == nullptr) {
+        return PTB_ERR_ARGUMENT;
+    }
+    PTB_GROUP(ctx, ptb_trace_paths(multi_root(ctx), seed, x, y, sx, sy, sample, count, trail_len, trail_out));
+    int rc = require_ready(ctx, false, false);
+    if(rc != PTB_OK) {
+        return rc;
+    }
+    if(ctx->width <= 0) {
+        return fail(ctx, PTB_ERR_STATE, "no image: call ptb_set_image first");
+    }
+    if(x == nullptr || y == nullptr || sx == nullptr || sy == nullptr || sample == nullptr || trail_out == nullptr ||
+       trail_len < 1 || trail_len > 100 || count > (1u << 26)) {
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_paths: null pointer, or trail_len outside 1..100");
+    }
+    for(size_t i = 0; i < count; ++i) {
+        if(x[i] >= static_cast<uint32_t>(ctx->width) || y[i] >= static_cast<uint32_t>(ctx->height) ||
+           sx[i] >= static_cast<uint32_t>(ctx->ns) || sy[i] >= static_cast<uint32_t>(ctx->ns)) {
+            return fail(ctx, PTB_ERR_ARGUMENT, "ptb_trace_paths: coordinate outside the image");
+        }
+    }
+    if(count == 0) {
+        return PTB_OK;
+    }
+    PTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t const st = ctx->stream;
+    uint32_t* d_in = nullptr;
+    int32_t* d_trail = nullptr;
+    size_t const cells = count * static_cast<size_t>(trail_len);
+    cudaError_t e = cudaMalloc(&d_in, 5 * count * sizeof(uint32_t));
+    e = e == cudaSuccess ? cudaMalloc(&d_trail, cells * sizeof(int32_t)) : e;
+    uint32_t const* srcs[5] = { x, y, sx, sy, sample };
+    for(int k = 0; k < 5 && e == cudaSuccess; ++k) {
+        e = cudaMemcpyAsync(d_in + static_cast<size_t>(k) * count, srcs[k], count * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    }
+    ProbeParams q{};
+    q.key = seed_key(seed);
+    q.width = static_cast<uint32_t>(ctx->width);
+    q.height = static_cast<uint32_t>(ctx->height);
+    q.ns = static_cast<uint32_t>(ctx->ns);
+    q.x = d_in;
+    q.y = d_in + count;
+    q.sx = d_in + 2 * count;
+    q.sy = d_in + 3 * count;
+    q.sample = d_in + 4 * count;
+    q.count = static_cast<uint32_t>(count);
+    e = e == cudaSuccess ? launch_trail_f64(q, ctx->d_spheres, ctx->n, ctx->d_camera, d_trail, trail_len, st) : e;
+    e = e == cudaSuccess ? cudaMemcpyAsync(trail_out, d_trail, cells * sizeof(int32_t), cudaMemcpyDeviceToHost, st) : e;
+    e = e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+    cudaFree(d_in);
+    cudaFree(d_trail);
+    ctx->stats.kernel_launches += 1;
+    if(e != cudaSuccess) {
+        return fail_cuda(ctx, e, "ptb_trace_paths");
+    }
+    return PTB_OK;
+}
+
 int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_t const* sample, size_t count,
                   int n_draws, double* draws_out)
 {

@@ -145,6 +145,8 @@ __device__ __forceinline__ Ray64 specular_ray(Hit64 const& h, V3 d, Rng64& rng)
 struct Counters64
 {
     uint32_t rays, diffuse, specular, dielectric;
+    int32_t* trail = nullptr; // parity tooling (ptb_trace_paths): sphere hit at each depth < trail_len, -1 = sky
+    int trail_len = 0;
 };
 
 __device__ V3 radiance(RawSphere const* __restrict__ sph, int n, Ray64 r, Rng64& rng, Counters64& cnt)
@@ -155,7 +157,11 @@ __device__ V3 radiance(RawSphere const* __restrict__ sph, int n, Ray64 r, Rng64&
         double t = 0.0;
         int id = 0;
         cnt.rays++;
-        if(!scene_intersect(sph, n, r, t, id)) {
+        bool const any_hit = scene_intersect(sph, n, r, t, id);
+        if(depth < cnt.trail_len) {
+            cnt.trail[depth] = any_hit ? id : -1;
+        }
+        if(!any_hit) {
             V3 const unit = norm(r.d);
             double const tt = 0.5 * (unit.y + 1.0);
             V3 const background = mk(1.0, 1.0, 1.0) * (1.0 - tt) + mk(0.5, 0.7, 1.0) * tt;
@@ -292,6 +298,31 @@ __global__ void probe_f64_kernel(ProbeParams const q, RawSphere const* __restric
     }
 }
 
+// The sequence of spheres a sample's path visits (depth by depth), for classifying the samples whose radiance differs
+// from the oracle's: same arithmetic as probe_f64_kernel, nothing else recorded.
+__global__ void trail_f64_kernel(ProbeParams const q, RawSphere const* __restrict__ sph, int n,
+                                 RawCamera const* __restrict__ camp, int32_t* __restrict__ trail, int trail_len)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= q.count) {
+        return;
+    }
+    RawCamera const cam = *camp;
+    uint32_t const x = q.x[i], y = q.y[i], sx = q.sx[i], sy = q.sy[i];
+    uint32_t const slot = ((y * q.width + x) * q.ns + sy) * q.ns + sx;
+    Rng64 rng;
+    rng.g = rng_open(q.key, slot, q.sample[i]);
+    rng.draws = 0;
+    Ray64 const pr = primary_ray(cam, x, y, sx, sy, q.width, q.height, q.ns, rng);
+    Counters64 cnt{ 0, 0, 0, 0 };
+    cnt.trail = trail + static_cast<size_t>(i) * static_cast<size_t>(trail_len);
+    cnt.trail_len = trail_len;
+    for(int d = 0; d < trail_len; ++d) {
+        cnt.trail[d] = -2; // depth never reached
+    }
+    (void)radiance(sph, n, pr, rng, cnt);
+}
+
 // One thread per sub-pixel slot, samples in index order: the accumulation order is
 // fixed, so the FP64 image is reproducible run to run.
 __global__ void render_f64_kernel(uint64_t key, uint32_t first_sample, uint32_t samples, uint32_t width, uint32_t height,
@@ -339,6 +370,16 @@ __global__ void render_f64_kernel(uint64_t key, uint32_t first_sample, uint32_t 
 }
 
 } // namespace
+
+cudaError_t launch_trail_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam, int32_t* trail,
+                             int trail_len, cudaStream_t stream)
+{
+    if(p.count == 0) {
+        return cudaSuccess;
+    }
+    trail_f64_kernel<<<(p.count + 127) / 128, 128, 0, stream>>>(p, spheres, n, cam, trail, trail_len);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_probe_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam,
                              cudaStream_t stream)

@@ -118,6 +118,8 @@ cudaError_t launch_smallpt_render_f64(uint64_t key, uint32_t first_sample, uint3
 // ---- FP64 parity path (reference operation order, no FMA contraction) ----------------------------------
 cudaError_t launch_probe_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam,
                              cudaStream_t stream);
+cudaError_t launch_trail_f64(ProbeParams const& p, RawSphere const* spheres, int n, RawCamera const* cam, int32_t* trail,
+                             int trail_len, cudaStream_t stream);
 cudaError_t launch_render_f64(uint64_t key, uint32_t first_sample, uint32_t samples, uint32_t width, uint32_t height,
                               uint32_t ns, RawSphere const* spheres, int n, RawCamera const* cam, double* accum64,
                               DeviceCounters* counters, cudaStream_t stream);

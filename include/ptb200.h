@@ -255,6 +255,13 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
                       uint32_t const* sy, uint32_t const* sample, size_t count, uint32_t flags, int32_t* primary_hit_out,
                       double* radiance_out, double* ray_out, uint32_t* draws_out);
 
+/* Parity probe, second part: which sphere each of the `count` samples' paths hits at depth 0, 1, ... trail_len-1
+ * (FP64 deterministic mode, src/ integrator): trail_out[count*trail_len], -1 = the ray left to the sky, -2 = the path
+ * had ended before.  For classifying samples whose radiance differs from the oracle's: a path is bit-exact as long as
+ * it only met mirrors (+ - * / sqrt); after a diffuse or glass bounce it carries libm-vs-CUDA sin/cos/pow ulps. */
+int ptb_trace_paths(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,
+                    uint32_t const* sy, uint32_t const* sample, size_t count, int trail_len, int32_t* trail_out);
+
 /* Raw uniforms of the counter stream for (seed, slot, sample): draws_out[count*n_draws]
  * as doubles, generated ON THE DEVICE.  For checking the stream against oracle/ptb_rng.h. */
 int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_t const* sample, size_t count,

@@ -123,6 +123,18 @@ class Oracle:
             *[_ptr(a) for a in arrs], int(count), _ptr(hit), _ptr(rad), _ptr(ray), _ptr(draws))
         return hit, rad, ray, draws
 
+    def trails(self, spheres, camera, width, height, nsub, seed, xs, ys, sxs, sys_, samples, trail_len=32):
+        """[count, trail_len] sphere index at each depth of each sample's path (-1 sky, -2 path over); port only."""
+        assert self.kind == "port"
+        spheres = np.ascontiguousarray(spheres).view(np.uint8).reshape(-1, SPHERE_BYTES)
+        camera = np.ascontiguousarray(camera).view(np.uint8)
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (xs, ys, sxs, sys_, samples)]
+        count = arrs[0].size
+        trail = np.zeros((count, trail_len), dtype=np.int32)
+        self.lib.orc_trails(_ptr(spheres), len(spheres), _ptr(camera), int(width), int(height), int(nsub),
+                            ctypes.c_uint64(seed), *[_ptr(a) for a in arrs], int(count), int(trail_len), _ptr(trail))
+        return trail
+
     def render(self, spheres, camera, width, height, samps, nsub=2, seed=1, first_sample=0, nthreads=0,
                want_sums=False):
         assert self.kind in ("port", "ref_ctr")

@@ -141,6 +141,8 @@ static uint64_t g_stats[ORC_STAT_COUNT];
 typedef struct stats
 {
     uint64_t c[ORC_STAT_COUNT];
+    int32_t* trail; /* orc_trails only: sphere hit at each depth < trail_len (-1 = sky); NULL otherwise */
+    int trail_len;
 } stats;
 
 static void stats_merge(stats const* s)
@@ -300,7 +302,11 @@ static v3 radiance(orc_sphere const* sph, int n, ray const* primary, rng* g, sta
         double closest_distance = 0.0;
         int object_index = 0;
 
-        if(!scene_intersect(sph, n, &r, &closest_distance, &object_index, st)) {
+        int const any_hit = scene_intersect(sph, n, &r, &closest_distance, &object_index, st);
+        if(st->trail != NULL && depth < st->trail_len) {
+            st->trail[depth] = any_hit ? object_index : -1;
+        }
+        if(!any_hit) {
             v3 const unit_direction = v3_norm(r.d);
             double const t = 0.5 * (unit_direction.y + 1.0);
             v3 const background = v3_add(v3_scale(v3_make(1.0, 1.0, 1.0), 1.0 - t), v3_scale(v3_make(0.5, 0.7, 1.0), t));
@@ -490,6 +496,38 @@ void orc_samples(void const* spheres, int n, void const* camera, int width, int 
             st.c[ORC_STAT_DRAWS] += g.draws;
         }
         stats_merge(&st);
+    }
+}
+
+/* Which sphere each sample's path hits at depth 0 .. trail_len-1 (-1 = sky, -2 = path over): the same calls as
+ * orc_samples, recording object_index of src/main.cpp:114.  For classifying samples that differ from the CUDA path. */
+void orc_trails(void const* spheres, int n, void const* camera, int width, int height, int num_subpixels, uint64_t seed,
+                uint32_t const* xs, uint32_t const* ys, uint32_t const* sxs, uint32_t const* sys, uint32_t const* samples,
+                int count, int trail_len, int32_t* trail_out)
+{
+    orc_sphere const* sph = (orc_sphere const*)spheres;
+    orc_camera cam;
+    memcpy(&cam, camera, sizeof(cam));
+#pragma omp parallel
+    {
+        stats st;
+        rng g;
+        memset(&g, 0, sizeof(g));
+#pragma omp for schedule(static)
+        for(int i = 0; i < count; ++i) {
+            memset(&st, 0, sizeof(st));
+            st.trail = trail_out + (size_t)i * (size_t)trail_len;
+            st.trail_len = trail_len;
+            for(int d = 0; d < trail_len; ++d) {
+                st.trail[d] = -2;
+            }
+            ptb_rng_key(&g.ctr, seed, slot_of((int)xs[i], (int)ys[i], (int)sxs[i], (int)sys[i], width, num_subpixels),
+                        samples[i]);
+            g.draws = 0;
+            ray const pr = primary_ray(&cam, (int)xs[i], (int)ys[i], (int)sxs[i], (int)sys[i], width, height,
+                                       num_subpixels, &g);
+            (void)radiance(sph, n, &pr, &g, &st);
+        }
     }
 }
 

@@ -104,6 +104,10 @@ void orc_samples(void const* spheres, int n, void const* camera, int width, int 
                  uint32_t const* samples, int count, int32_t* primary_hit, double* radiance_out, double* ray_out,
                  uint64_t* draws_out);
 
+/* Sphere index hit at each depth of each sample's path: trail_out[count*trail_len], -1 = sky, -2 = path over. */
+void orc_trails(void const* spheres, int n, void const* camera, int width, int height, int num_subpixels, uint64_t seed,
+                uint32_t const* xs, uint32_t const* ys, uint32_t const* sxs, uint32_t const* sys, uint32_t const* samples,
+                int count, int trail_len, int32_t* trail_out);
 void orc_render(void const* spheres, int n, void const* camera, int width, int height, int samps,
                 int num_subpixels, uint64_t seed, uint32_t first_sample, double* image_out, double* sums_out,
                 int nthreads);

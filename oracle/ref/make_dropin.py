@@ -4,7 +4,7 @@
     python oracle/ref/make_dropin.py /root/reference/src/main.cpp /tmp/build/main_dropin.cpp
 
 Everything that builds the scene, the camera and the PPM file is kept; the taskflow row-task block
-(src/main.cpp:214-236) becomes seven calls into include/ptb200.h.  oracle/Makefile compiles the result with the
+(src/main.cpp:214-236) becomes eight calls into include/ptb200.h (every GPU of the box behind one context).  oracle/Makefile compiles the result with the
 reference's own headers and translation units into oracle/_ref/cpu_path_tracer_b200 -- the reference PROGRAM running
 on the B200 library -- which tests/test_reference_dropin.py links-checks on CPU and runs on the GPU box.
 """
@@ -13,8 +13,18 @@ import sys
 
 ABI_BLOCK = '''    static_assert(sizeof(pt::sphere) == PTB_SPHERE_BYTES && sizeof(pt::camera) == PTB_CAMERA_BYTES,
                   "the reference's own records cross the boundary as they are");
+    // every GPU of the machine, as the reference's executor uses every core; PTB_GPUS=n caps it
+    int devices[16];
+    int n_gpus = ptb_device_count() < 16 ? ptb_device_count() : 16;
+    if(char const* cap = std::getenv("PTB_GPUS")) {
+        n_gpus = std::atoi(cap) < n_gpus ? std::atoi(cap) : n_gpus;
+    }
+    n_gpus = n_gpus < 1 ? 1 : n_gpus; // none: let the library say so
+    for(int i = 0; i < n_gpus; ++i) {
+        devices[i] = i;
+    }
     ptb_context* gpu = nullptr;
-    if(ptb_create(/*device*/ 0, &gpu) != PTB_OK) {
+    if(ptb_create_multi(devices, n_gpus, &gpu) != PTB_OK) {
         std::cerr << ptb_last_error(nullptr) << '\\n';
         return 1;
     }
@@ -36,7 +46,7 @@ ABI_BLOCK = '''    static_assert(sizeof(pt::sphere) == PTB_SPHERE_BYTES && sizeo
 def patch(text: str) -> str:
     if "#include <taskflow/taskflow.hpp>" not in text:
         raise SystemExit("make_dropin: taskflow include not found -- has the reference changed?")
-    text = text.replace("#include <taskflow/taskflow.hpp>", "#include <ptb200.h> // C ABI of the B200 render loop")
+    text = text.replace("#include <taskflow/taskflow.hpp>", "#include <ptb200.h> // C ABI of the B200 render loop\n#include <cstdlib>")
     block = re.compile(r"^    tf::Executor executor\{\};\n.*?^    executor\.run\(taskflow\)\.wait\(\);\n", re.S | re.M)
     text, n = block.subn(lambda _m: ABI_BLOCK, text)
     if n != 1:

@@ -8,7 +8,7 @@ Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from conftest import make_renderer
+from conftest import classify_outliers, make_renderer
 
 pytestmark = pytest.mark.gpu
 
@@ -32,13 +32,17 @@ def test_fp64_samples_against_reference_golden(gpu, golden, golden_scene, name):
     z = golden(f"samples_{name}.npz")
     W, H = int(z["width"]), int(z["height"])
     sph, _, cam = golden_scene(name, W, H)
+    from oracle import Oracle
     with make_renderer(gpu, sph, cam, W, H, int(z["nsub"])) as r:
         hit, rad, ray, draws = r.trace_samples(int(z["seed"]), z["x"], z["y"], z["sx"], z["sy"], z["sample"],
                                                gpu.PRECISION_FP64)
+        # every sample outside 1e-4 is accounted for: same spheres as the reference's path through a diffuse / glass bounce
+        n_bad, n_div = classify_outliers(gpu, Oracle("port"), r, sph, cam, W, H, int(z["nsub"]), int(z["seed"]), z["x"], z["y"],
+                                         z["sx"], z["sy"], z["sample"], rad, z["radiance"], REL_TOL)
+    print(f"{name}: {n_bad} of {len(rad)} samples outside {REL_TOL} (all after a diffuse/glass bounce; {n_div} change spheres later)")
     assert np.array_equal(hit, z["hit"]), "primary-hit indices must be bit-exact"
     assert np.array_equal(ray, z["ray"]), "camera rays use only + - * / sqrt: bit-exact"
-    rel = rel_err(rad, z["radiance"])
-    assert (rel <= REL_TOL).mean() >= 0.999, f"{(rel > REL_TOL).sum()} of {len(rel)} samples off by more than {REL_TOL}"
+    assert n_bad <= 1e-3 * len(rad)
     assert (draws == z["draws"]).mean() >= 0.999
 
 
@@ -52,10 +56,11 @@ def test_fp64_samples_against_oracle(gpu, oracle_port, name):
     ohit, orad, oray, odraws = oracle_port.samples(sph, cam, W, H, 2, 99, xs, ys, sx, sy, ss)
     with make_renderer(gpu, sph, cam, W, H) as r:
         hit, rad, ray, draws = r.trace_samples(99, xs, ys, sx, sy, ss, gpu.PRECISION_FP64)
+        n_bad, n_div = classify_outliers(gpu, oracle_port, r, sph, cam, W, H, 2, 99, xs, ys, sx, sy, ss, rad, orad, REL_TOL)
+    print(f"{name}: {n_bad} of {n} samples outside {REL_TOL} (all after a diffuse/glass bounce; {n_div} change spheres later)")
     assert np.array_equal(hit, ohit)
     assert np.array_equal(ray, oray)
-    rel = rel_err(rad, orad)
-    assert (rel <= REL_TOL).mean() >= 0.999
+    assert n_bad <= 1e-3 * n
     # mirror-only paths touch nothing but + - * / sqrt: most samples are bit-identical
     assert (rad == orad).all(axis=1).mean() > 0.9
     assert (draws == odraws).mean() >= 0.999

@@ -1,5 +1,5 @@
 """The drop-in claim, end to end: the REFERENCE'S OWN PROGRAM -- src/main.cpp with the
-INTEGRATION.md patch (its taskflow row tasks replaced by seven calls into include/ptb200.h), compiled against the
+INTEGRATION.md patch (its taskflow row tasks replaced by calls into include/ptb200.h, every GPU of the box behind one context), compiled against the
 reference's unmodified headers and translation units -- runs on libptb200.so and writes the image the library's own
 host program writes.  oracle/Makefile builds it where /root/reference exists (oracle/ref/make_dropin.py applies the
 patch in a scratch directory); the binary travels to the GPU box, the sources do not."""
@@ -31,8 +31,8 @@ def test_reference_program_binds_only_the_abi():
     assert "libptb200.so" in dyn
     und = subprocess.run(["nm", "-D", "--undefined-only", EXE], capture_output=True, text=True, check=True).stdout
     bound = sorted(l.split()[-1] for l in und.splitlines() if " ptb_" in l)
-    assert bound == ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_render", "ptb_resolve", "ptb_set_camera",
-                     "ptb_set_image", "ptb_upload_scene"]
+    assert bound == ["ptb_create_multi", "ptb_destroy", "ptb_device_count", "ptb_last_error", "ptb_render", "ptb_resolve",
+                     "ptb_set_camera", "ptb_set_image", "ptb_upload_scene"]
     assert "tf::" not in und and "omp_" not in und  # no task pool left behind
 
 
@@ -73,6 +73,26 @@ def test_reference_program_renders_through_the_library(tmp_path):
     assert np.abs(img_a - img_b).max() <= 1
     assert (img_a == img_b).mean() > 0.999
     assert img_a.mean() > 20  # and it is a picture, not a black frame
+
+
+@needs_exe
+@pytest.mark.gpu
+def test_reference_program_on_every_gpu_writes_the_one_gpu_image(tmp_path):
+    """The patched program takes every GPU of the box behind ONE context (ptb_create_multi); PTB_GPUS=1 caps it.  The
+    stream is keyed by the absolute sample index: the picture must not depend on the GPU count."""
+    import ctypes
+    n = ctypes.CDLL(os.path.join(ROOT, "cpu-path-tracing_b200", "libptb200.so")).ptb_device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    imgs = []
+    for cap in ("1", str(n)):
+        d = tmp_path / cap
+        d.mkdir()
+        out = subprocess.run([EXE, "64"], cwd=d, capture_output=True, text=True, env=dict(os.environ, PTB_GPUS=cap))
+        assert out.returncode == 0, out.stderr
+        imgs.append(read_ppm(d / "image.ppm")[0])
+    assert np.abs(imgs[0] - imgs[1]).max() <= 1 and (imgs[0] == imgs[1]).mean() > 0.999
+    assert imgs[0].mean() > 20
 
 
 needs_sb = pytest.mark.skipif(not os.path.exists(SB_EXE), reason="oracle/_ref/smallpt_b200 not built (no /root/reference here)")
