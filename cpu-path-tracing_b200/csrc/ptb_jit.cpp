@@ -1,6 +1,7 @@
 // ptb_jit.cpp -- see ptb_jit.hpp.  Host code only; NVRTC and the driver API are reached through dlopen.
 #include "ptb_jit.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -255,8 +256,25 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
     if(a.AddNameExpression(prog, name.c_str()) != NVRTC_SUCCESS) {
         return fail("nvrtcAddNameExpression failed");
     }
-    char const* opts[] = { "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo" };
-    nvrtcResult const rc = a.CompileProgram(prog, 3, opts);
+    // development knobs (dev/ab_bench.py, dev/jit_offline.py): PTB_JIT_DEFINES="-DPTB_X=1 -DPTB_Y" adds macro definitions to this
+    // process's run-time builds (A/B of #ifdef'ed experiments with ONE library), PTB_JIT_DUMP=dir keeps the generated
+    // translation unit, the kernel's name and the cubin
+    std::vector<std::string> extra;
+    if(char const* defs = std::getenv("PTB_JIT_DEFINES")) {
+        std::string const d = defs;
+        for(size_t pos = 0; pos < d.size();) {
+            size_t const sp = std::min(d.find(' ', pos), d.size());
+            if(sp > pos) {
+                extra.push_back(d.substr(pos, sp - pos));
+            }
+            pos = sp + 1;
+        }
+    }
+    std::vector<char const*> opts = { "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo" };
+    for(std::string const& e : extra) {
+        opts.push_back(e.c_str());
+    }
+    nvrtcResult const rc = a.CompileProgram(prog, static_cast<int>(opts.size()), opts.data());
     if(rc != NVRTC_SUCCESS) {
         size_t n = 0;
         a.GetProgramLogSize(prog, &n);
@@ -283,6 +301,21 @@ JitKernel const* JitCache::get(ConstSceneF32 const& cs, SceneCounts const& c, Ki
         a.GetErrorString(e, &s);
         return fail(std::string(what) + ": " + (s != nullptr ? s : "unknown driver error"));
     };
+    if(char const* dir = std::getenv("PTB_JIT_DUMP")) {
+        std::string const base = std::string(dir) + "/jit_" + std::to_string(compiled_ + failures_) + "_" + std::to_string(static_cast<int>(kind));
+        if(std::FILE* f = std::fopen((base + ".cu").c_str(), "wb")) {
+            std::fwrite(tu.data(), 1, tu.size(), f);
+            std::fclose(f);
+        }
+        if(std::FILE* f = std::fopen((base + ".name").c_str(), "wb")) {
+            std::fwrite(name.data(), 1, name.size(), f);
+            std::fclose(f);
+        }
+        if(std::FILE* f = std::fopen((base + ".cubin").c_str(), "wb")) {
+            std::fwrite(cubin.data(), 1, cubin.size(), f);
+            std::fclose(f);
+        }
+    }
     CUmodule mod = nullptr;
     CUresult e = a.ModuleLoadData(&mod, cubin.data());
     if(e != CUDA_SUCCESS) {

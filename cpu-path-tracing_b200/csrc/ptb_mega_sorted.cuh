@@ -44,16 +44,17 @@ constexpr int kSortedBlocksPerSm = PTB_SORTED_BLOCKS; // dev/build_variant.sh ex
 #else
 constexpr int kSortedBlocksPerSm = 6;
 #endif
-constexpr int kSortedRing = 64;     // entries per ring, power of two
+constexpr int kSortedPool = 64;     // entries per pool
 constexpr int kEmissiveBit = 0x100; // in ShadePlanes::b.w next to the reflection tag (ptb_api.cpp: pack_geometry)
+constexpr uint32_t kNoSphere = 0x00FFFFFFu; // low 24 bits of the depth | sphere word of a camera ray (sign-extends to -1)
 
-// Byte layout of one warp's pool: two rings x four planes of float4[kSortedRing]
+// Byte layout of one warp's pools: two stacks x four planes of 16-byte cells [kSortedPool]
 //   plane a = origin xyz, len           plane b = direction xyz, slot
-//   plane c = throughput rgb, last      plane d = rng.state, rng.inc, depth, material
-constexpr uint32_t kPlaneBytes = kSortedRing * 16u;
-constexpr uint32_t kRingBytes = 4u * kPlaneBytes;
-constexpr uint32_t kPoolBytes = 2u * kRingBytes;  // READY at +0, PARK at +kRingBytes
-constexpr uint32_t kRingMask = kPlaneBytes - 16u; // byte offset of an entry inside a plane, wraps
+//   plane c = throughput rgb, depth << 24 | sphere the ray starts on        plane d = rng.state, rng.inc (8 of the 16 bytes:
+//   one address register + immediate plane offsets serve all four accesses of an entry)
+constexpr uint32_t kPlaneBytes = kSortedPool * 16u;
+constexpr uint32_t kStackBytes = 4u * kPlaneBytes;
+constexpr uint32_t kPoolBytes = 2u * kStackBytes; // READY at +0, PARK at +kStackBytes
 
 // Explicit shared-window accesses: a 32-bit address register + immediate plane offset per access
 // (through generic pointers the compiler re-derives the window base in every loop iteration).
@@ -66,6 +67,16 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 __device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w)
 {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" : : "r"(addr), "r"(x), "r"(y) : "memory");
 }
 
 template<class Shape, bool kSmemShade, int kInline>
@@ -103,7 +114,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     uint32_t const lane_bit = 1u << lane;
     uint32_t const lt_mask = lane_bit - 1u;
     uint32_t const ready_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pool)) + (threadIdx.x >> 5) * kPoolBytes;
-    uint32_t const park_base = ready_base + kRingBytes;
+    uint32_t const park_base = ready_base + kStackBytes;
 #ifdef PTB_JIT_SCENE_INIT
     // Run-time compiled build (ptb_jit.cpp): the scene's coefficients arrive as LITERALS and fold into immediates of
     // the FFMA / FADD instructions -- no uniform loads in the scan, no register-file bandwidth for them either.
@@ -114,10 +125,12 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     float const k_uniform = Shape::uniform_k ? scene.big_geo[0].k : 0.0f;
     uint32_t const keep_reg = prm.key_mask; // see closest_hit: a run-time value so that it stays in a register
 
-    // warp-uniform state; ring positions are BYTE offsets inside a plane (multiples of 16, wrapped with kRingMask)
+    // warp-uniform state.  Both pools are STACKS: one byte offset each (16 x the number of entries), no wrap-around and
+    // no tail pointer.  Which ray a lane takes next does not matter -- the stream travels with the path -- and what is
+    // left at the bottom of READY is traced when the tiles run out.
     uint32_t tile_sample0 = 0, tile_samples = 0, next_sample = 0;
-    uint32_t ready_head = 0, ready_tail = 0, ready_count = 0;
-    uint32_t park_head = 0, park_tail = 0, park_count = 0;
+    uint32_t ready_top = 0, park_top = 0;
+    int refill_level = 32 * 16; // camera samples are generated while READY + PARK hold <= 32 entries; -1 once the tiles are gone
     bool exhausted = false;
     // per lane: the sub-pixel this lane generates camera samples for in the current tile
     uint32_t gen_slot = 0, gen_valid = 0, gen_x = 0, gen_y = 0, gen_sx = 0, gen_sy = 0;
@@ -126,6 +139,10 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     // common case -- every lane busy -- is one compare.
     uint32_t am = 0u;
     uint32_t slot = 0;
+    // depth and the sphere the ray starts on share one word, depth << 24 | sphere (kNoSphere for a camera ray): the path
+    // state is 14 words -- three 16-byte planes and one 8-byte plane -- and the bounce never unpacks it: "depth > 4" and
+    // "depth < 99" are unsigned compares of the whole word, ++depth adds 1 << 24, a hit replaces the low 24 bits
+    uint32_t dl = kNoSphere;
     PathF32 p;
     p.er = p.eg = p.eb = 0.0f; // unused here: emission is flushed where it is picked up
     p.ox = p.oy = p.oz = p.dx = p.dy = p.dz = p.len = p.tr = p.tg = p.tb = 0.0f;
@@ -134,16 +151,17 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
     p.last = -1;
     BounceCounters cnt{ 0, 0, 0, 0 };
 
-    // lanes of `need` take the oldest READY entries, lowest lane first; returns the new "holds a ray" mask
+    // lanes of `need` take the top READY entries, lowest lane first; returns the new "holds a ray" mask
     auto const pop = [&](uint32_t need) -> uint32_t {
-        uint32_t const rank = __popc(need & lt_mask);
-        bool const take = (need & lane_bit) != 0u && rank < ready_count;
+        uint32_t const rank16 = __popc(need & lt_mask) * 16u;
+        bool const take = (need & lane_bit) != 0u && rank16 < ready_top;
         if(take) {
-            uint32_t const rd = ready_base + ((ready_tail + rank * 16u) & kRingMask);
+            uint32_t const at = ready_top - 16u - rank16;
+            uint32_t const rd = ready_base + at;
             float4 const ea = lds128(rd);
             float4 const eb = lds128(rd + kPlaneBytes);
             float4 const ec = lds128(rd + 2u * kPlaneBytes);
-            float4 const ed = lds128(rd + 3u * kPlaneBytes);
+            uint2 const ed = lds64(rd + 3u * kPlaneBytes);
             p.ox = ea.x;
             p.oy = ea.y;
             p.oz = ea.z;
@@ -155,37 +173,44 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
             p.tr = ec.x;
             p.tg = ec.y;
             p.tb = ec.z;
-            p.last = __float_as_int(ec.w);
-            p.rng.state = __float_as_uint(ed.x);
-            p.rng.inc = __float_as_uint(ed.y);
-            p.depth = __float_as_int(ed.z);
+            dl = __float_as_uint(ec.w);
+            p.rng.state = ed.x;
+            p.rng.inc = ed.y;
         }
-        uint32_t const wanted = static_cast<uint32_t>(__popc(need));
-        uint32_t const taken = min(wanted, ready_count);
-        ready_tail = (ready_tail + taken * 16u) & kRingMask;
-        ready_count -= taken;
+        uint32_t const wanted = static_cast<uint32_t>(__popc(need)) * 16u;
+        uint32_t const taken = min(wanted, ready_top);
+        ready_top -= taken;
         return taken == wanted ? kFull : (~need | __ballot_sync(kFull, take));
+    };
+    // one complete path state into a pool at byte offset `at` (16 x entry index)
+    auto const push = [&](uint32_t base, uint32_t at, PathF32 const& q, uint32_t q_slot, float tr, float tg, float tb, uint32_t q_dl) {
+        sts128(base + at, q.ox, q.oy, q.oz, q.len);
+        sts128(base + at + kPlaneBytes, q.dx, q.dy, q.dz, __uint_as_float(q_slot));
+        sts128(base + at + 2u * kPlaneBytes, tr, tg, tb, __uint_as_float(q_dl));
+        sts64(base + at + 3u * kPlaneBytes, q.rng.state, q.rng.inc);
     };
 
     for(;;) {
-        // ================= slow path: ring maintenance, a few percent of the iterations ===========================
-        if(am != kFull || park_count >= 32u || (!exhausted && ready_count + park_count <= 32u)) {
+        // ================= slow path: pool maintenance, a few percent of the iterations ===========================
+        bool const park_full = park_top >= 32u * 16u;
+        if(am != kFull || park_full || static_cast<int>(ready_top + park_top) <= refill_level) {
             // ---- scatter stage: up to 32 parked paths, one per lane -------------------------------------------
-            if(park_count >= 32u || (am != kFull && exhausted && ready_count == 0u && park_count != 0u)) {
+            if(park_full || (am != kFull && exhausted && ready_top == 0u && park_top != 0u)) {
                 __syncwarp(); // the parked entries were written by other lanes
-                uint32_t const k = min(32u, park_count);
+                uint32_t const k16 = min(32u * 16u, park_top);
                 bool out = false;
                 PathF32 q;
                 q.ox = q.oy = q.oz = q.dx = q.dy = q.dz = q.len = 0.0f;
                 q.rng.state = q.rng.inc = 0u;
                 float4 eb = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ec = eb;
-                int depth1 = 0;
-                if(lane < k) {
-                    uint32_t const rd = park_base + ((park_tail + lane * 16u) & kRingMask);
+                uint32_t dl1 = 0u;
+                if(lane * 16u < k16) {
+                    uint32_t const at = park_top - k16 + lane * 16u;
+                    uint32_t const rd = park_base + at;
                     float4 const ea = lds128(rd);
                     eb = lds128(rd + kPlaneBytes);
                     ec = lds128(rd + 2u * kPlaneBytes);
-                    float4 const ed = lds128(rd + 3u * kPlaneBytes);
+                    uint2 const ed = lds64(rd + 3u * kPlaneBytes);
                     q.ox = ea.x;
                     q.oy = ea.y;
                     q.oz = ea.z;
@@ -193,13 +218,15 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     q.dx = eb.x;
                     q.dy = eb.y;
                     q.dz = eb.z;
-                    q.rng.state = __float_as_uint(ed.x);
-                    q.rng.inc = __float_as_uint(ed.y);
-                    int const last = __float_as_int(ec.w);
-                    int const mat = __float_as_int(ed.w);
-                    depth1 = __float_as_int(ed.z) + 1; // main.cpp:111 ++depth
-                    // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6)
+                    q.rng.state = ed.x;
+                    q.rng.inc = ed.y;
+                    uint32_t const qdl = __float_as_uint(ec.w);
+                    int const last = static_cast<int>(qdl & kNoSphere);
+                    dl1 = qdl + (1u << 24); // main.cpp:111 ++depth
+                    // outward normal at the hit point, as in the bounce that parked the path (hit_record.cpp:6); the
+                    // material is the sphere's: read back from its shading plane rather than carried through the pool
                     float4 const sa = shade(0, last);
+                    int const mat = __float_as_int(shade(1, last).w) & 0xff;
                     float nx, ny, nz;
                     unit_normal(q.ox, q.oy, q.oz, sa, nx, ny, nz);
                     float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
@@ -217,30 +244,23 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                         scatter_dielectric(q, nx, ny, nz, dn);
                     }
                     // the ray scattered by the last iteration is never traced (main.cpp:111): the path ends here
-                    out = depth1 < kDepthLimit;
+                    out = dl1 < (static_cast<uint32_t>(kDepthLimit) << 24);
                     if(!out) {
                         red_add_v4(prm.accum + __float_as_uint(eb.w), 0.0f, 0.0f, 0.0f, 1.0f);
                     }
                 }
                 uint32_t const om = __ballot_sync(kFull, out);
                 if(out) {
-                    uint32_t const w = ready_base + ((ready_head + __popc(om & lt_mask) * 16u) & kRingMask);
-                    sts128(w, q.ox, q.oy, q.oz, q.len);
-                    sts128(w + kPlaneBytes, q.dx, q.dy, q.dz, eb.w);
-                    sts128(w + 2u * kPlaneBytes, ec.x, ec.y, ec.z, ec.w);
-                    sts128(w + 3u * kPlaneBytes, __uint_as_float(q.rng.state), __uint_as_float(q.rng.inc), __int_as_float(depth1), 0.0f);
+                    push(ready_base, ready_top + __popc(om & lt_mask) * 16u, q, __float_as_uint(eb.w), ec.x, ec.y, ec.z, dl1);
                 }
-                uint32_t const nout = static_cast<uint32_t>(__popc(om));
-                park_tail = (park_tail + k * 16u) & kRingMask;
-                park_count -= k;
-                ready_head = (ready_head + nout * 16u) & kRingMask;
-                ready_count += nout;
+                park_top -= k16;
+                ready_top += static_cast<uint32_t>(__popc(om)) * 16u;
                 __syncwarp();
             }
 
             // ---- refill: one camera sample per lane (main.cpp:186-190, camera.cpp:19-38) -----------------
-            if(!exhausted && ready_count + park_count <= 32u) {
-                __syncwarp(); // ring entries read by earlier pops are about to be overwritten
+            if(static_cast<int>(ready_top + park_top) <= refill_level) {
+                __syncwarp(); // entries read by earlier pops are about to be overwritten
                 if(next_sample >= tile_samples) {
                     unsigned long long t = 0;
                     if(lane == 0) {
@@ -249,6 +269,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     t = __shfl_sync(kFull, t, 0);
                     if(t >= prm.ntiles) {
                         exhausted = true;
+                        refill_level = -1;
                     }
                     else {
                         uint32_t const tile = static_cast<uint32_t>(t);
@@ -269,25 +290,20 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                         PathF32 g;
                         g.rng = rng_open(prm.key, gen_slot, prm.first_sample + tile_sample0 + next_sample);
                         gen_primary(g, prm.cams.cam, gen_x, gen_y, gen_sx, gen_sy);
-                        uint32_t const w = ready_base + ((ready_head + lane * 16u) & kRingMask);
-                        sts128(w, g.ox, g.oy, g.oz, g.len);
-                        sts128(w + kPlaneBytes, g.dx, g.dy, g.dz, __uint_as_float(gen_slot));
-                        sts128(w + 2u * kPlaneBytes, 1.0f, 1.0f, 1.0f, __int_as_float(-1));
-                        sts128(w + 3u * kPlaneBytes, __uint_as_float(g.rng.state), __uint_as_float(g.rng.inc), __int_as_float(0), 0.0f);
+                        push(ready_base, ready_top + lane * 16u, g, gen_slot, 1.0f, 1.0f, 1.0f, kNoSphere);
                     }
-                    ready_head = (ready_head + gen_valid * 16u) & kRingMask;
-                    ready_count += gen_valid;
+                    ready_top += gen_valid * 16u;
                     next_sample += 1u;
                     __syncwarp();
                 }
             }
 
             // ---- lanes that found READY empty at the end of their last bounce try again ---------------------
-            if(am != kFull && ready_count != 0u) {
+            if(am != kFull && ready_top != 0u) {
                 am = pop(~am);
             }
             if(am == 0u) {
-                if(exhausted && ready_count == 0u && park_count == 0u) {
+                if(exhausted && ready_top == 0u && park_top == 0u) {
                     break;
                 }
                 continue;
@@ -300,8 +316,10 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
         int state = 2;
         bool ended = false;
         bool const alive = (am & lane_bit) != 0u;
-        int material = 0;
         if(alive) {
+            if constexpr(Shape::generic || !Shape::embed) {
+                p.last = static_cast<int>(dl << 8) >> 8; // full-precision keys: the self-sphere root needs the list position
+            }
             RayTerms const r = ray_terms(p, k_uniform);
             float t;
             int id;
@@ -319,15 +337,14 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 p.ox = fmaf(p.dx, t, p.ox);
                 p.oy = fmaf(p.dy, t, p.oy);
                 p.oz = fmaf(p.dz, t, p.oz);
-                p.last = id;
+                // main.cpp:128-139 Russian roulette once depth > 4: p = max(color), survivor weight color / p
+                bool const roulette = dl >= (static_cast<uint32_t>(kRouletteThreshold + 1) << 24);
+                dl = (dl & ~kNoSphere) | static_cast<uint32_t>(id);
                 float4 const sb = shade(1, id);
                 int const tag = __float_as_int(sb.w);
-                material = tag & 0xff;
                 if((tag & kEmissiveBit) != 0) { // main.cpp:126
                     red_add_v4(prm.accum + slot, p.tr * sb.x, p.tg * sb.y, p.tb * sb.z, 0.0f);
                 }
-                // main.cpp:128-139 Russian roulette: p = max(color), survivor weight color / p
-                bool const roulette = p.depth > kRouletteThreshold;
                 float4 const col = shade(roulette ? 3 : 2, id);
                 if(roulette) {
                     ended = !(rng_uniform_f32(p.rng) < col.w);
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 if(ended) {
                     red_add_v4(prm.accum + slot, 0.0f, 0.0f, 0.0f, 1.0f);
                 }
-                else if(material == kInline && p.depth < kDepthLimit - 1) {
+                else if(((tag ^ kInline) & 0xff) == 0 && dl < (static_cast<uint32_t>(kDepthLimit - 1) << 24)) {
                     float4 const sa = shade(0, id);
                     float nx, ny, nz; // outward unit normal, hit_record.cpp:6
                     unit_normal(p.ox, p.oy, p.oz, sa, nx, ny, nz);
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                         bool const front = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz)) < 0.0f; // hit_record.cpp:7
                         scatter_diffuse(p, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
                     }
-                    p.depth++;
+                    dl += 1u << 24;
                     state = 0;
                 }
                 else {
@@ -366,16 +383,9 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
         uint32_t const need = __ballot_sync(kFull, state != 0);
         if(need != 0u) {
             if(park) {
-                uint32_t const w = park_base + ((park_head + __popc(pm & lt_mask) * 16u) & kRingMask);
-                sts128(w, p.ox, p.oy, p.oz, p.len);
-                sts128(w + kPlaneBytes, p.dx, p.dy, p.dz, __uint_as_float(slot));
-                sts128(w + 2u * kPlaneBytes, p.tr, p.tg, p.tb, __int_as_float(p.last));
-                sts128(w + 3u * kPlaneBytes, __uint_as_float(p.rng.state), __uint_as_float(p.rng.inc),
-                       __int_as_float(p.depth), __int_as_float(material));
+                push(park_base, park_top + __popc(pm & lt_mask) * 16u, p, slot, p.tr, p.tg, p.tb, dl);
             }
-            uint32_t const n = static_cast<uint32_t>(__popc(pm));
-            park_head = (park_head + n * 16u) & kRingMask;
-            park_count += n;
+            park_top += static_cast<uint32_t>(__popc(pm)) * 16u;
             am = pop(need);
         }
     }

@@ -232,7 +232,13 @@ __device__ __forceinline__ float small_disc_far(float cx, float cy, float cz, fl
 template<bool kBoth, bool kRobust = false>
 __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& p, RayTerms const& r, bool self = false)
 {
+#ifdef PTB_JIT_SCENE_INIT
+    // run-time build: a coordinate that IS zero (a literal) needs no subtraction -- "0 - o" does not fold by itself
+    // (signed zero), written as a negation it disappears into the operand modifiers of the FFMAs that follow
+    float const cx = s.cx == 0.0f ? -p.ox : s.cx - p.ox, cy = s.cy == 0.0f ? -p.oy : s.cy - p.oy, cz = s.cz == 0.0f ? -p.oz : s.cz - p.oz;
+#else
     float const cx = s.cx - p.ox, cy = s.cy - p.oy, cz = s.cz - p.oz; // c - o = -oc
+#endif
     float const nb = fmaf(cx, p.dx, fmaf(cy, p.dy, cz * p.dz));       // -half_b
     float disc;
     if constexpr(kRobust) {
@@ -300,7 +306,14 @@ __device__ __forceinline__ uint32_t key_big_axis(float ga, float K, float k, Pat
     float const da = AXIS == 0 ? p.dx : (AXIS == 1 ? p.dy : p.dz);
     float const oa2 = AXIS == 0 ? r.o2x : (AXIS == 1 ? r.o2y : r.o2z);
     float const hb = fmaf(da, ga, kUniformK ? r.kod : k * r.od);
+#ifdef PTB_JIT_SCENE_INIT
+    // run-time build: (2 o_a) * g = o_a * (2 g) bit for bit, and 2 g is a literal -- the doubled origin is never formed
+    float const oa = AXIS == 0 ? p.ox : (AXIS == 1 ? p.oy : p.oz);
+    float const cp = fmaf(oa, 2.0f * ga, kUniformK ? (K == 0.0f ? r.koo : r.koo + K) : fmaf(k, r.oo, K));
+    (void)oa2;
+#else
     float const cp = fmaf(oa2, ga, kUniformK ? r.koo + K : fmaf(k, r.oo, K));
+#endif
     float const disc = fmaf(hb, hb, -(k * cp));
     float const m = add_root(fabsf(hb), disc);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
@@ -323,7 +336,13 @@ __device__ __forceinline__ uint32_t key_big_pair(float ga, float K, float k, Pat
     float const G = fabsf(ga);
     uint32_t const sign = __float_as_uint(da) & 0x80000000u;
     float const hb = fmaf(-fabsf(da), G, r.kod);
+#ifdef PTB_JIT_SCENE_INIT
+    float const oa = AXIS == 0 ? p.ox : (AXIS == 1 ? p.oy : p.oz); // (2 o_a) * G = o_a * (2 G), 2 G a literal
+    float const cp = fmaf(-__uint_as_float(__float_as_uint(oa) ^ sign), 2.0f * G, r.koo + K);
+    (void)oa2;
+#else
     float const cp = fmaf(-__uint_as_float(__float_as_uint(oa2) ^ sign), G, r.koo + K);
+#endif
     float const disc = fmaf(hb, hb, -(k * cp));
     float const m = add_root(fabsf(hb), disc);
     uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;

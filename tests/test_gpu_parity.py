@@ -57,7 +57,11 @@ def test_fp64_samples_against_oracle(gpu, oracle_port, name):
     with make_renderer(gpu, sph, cam, W, H) as r:
         hit, rad, ray, draws = r.trace_samples(99, xs, ys, sx, sy, ss, gpu.PRECISION_FP64)
         n_bad, n_div = classify_outliers(gpu, oracle_port, r, sph, cam, W, H, 2, 99, xs, ys, sx, sy, ss, rad, orad, REL_TOL)
-    print(f"{name}: {n_bad} of {n} samples outside {REL_TOL} (all after a diffuse/glass bounce; {n_div} change spheres later)")
+        # the same statement at tolerance ZERO: a sample that is not bit-identical to the oracle's has met a diffuse or
+        # glass surface before the first difference -- mirror-only paths (+ - * / sqrt) are exact to the last bit
+        n_inexact, _ = classify_outliers(gpu, oracle_port, r, sph, cam, W, H, 2, 99, xs, ys, sx, sy, ss, rad, orad, 0.0)
+    print(f"{name}: {n_bad} of {n} samples outside {REL_TOL} (all after a diffuse/glass bounce; {n_div} change spheres later); "
+          f"{n_inexact} not bit-identical, every one of them after a diffuse/glass bounce")
     assert np.array_equal(hit, ohit)
     assert np.array_equal(ray, oray)
     assert n_bad <= 1e-3 * n
