@@ -264,6 +264,15 @@ __device__ __forceinline__ uint32_t key_small(SmallGeo const& s, PathF32 const& 
     return key;
 }
 
+// x with its sign flipped when hb >= 0 (sign bit clear): x ^ (~hb & 0x80000000) as ONE three-input logic op.  Left to the
+// compiler the expression becomes a negation (FADD) plus a LOP3 per sphere test.
+__device__ __forceinline__ float flip_unless_negative(float x, float hb)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD2;" : "=r"(r) : "r"(__float_as_uint(x)), "r"(__float_as_uint(hb)));
+    return __uint_as_float(r);
+}
+
 // Big-sphere form.  With m = sqrt(disc) + |hb| (no cancellation, m > 0) the two roots are
 //   sigma * c / m   and   sigma * m / k,     sigma = -sign(hb)  (+1 when approaching),
 // which is the numerically stable pairing for EITHER sign of hb: the earlier c/(sqrt - hb)
@@ -276,12 +285,11 @@ __device__ __forceinline__ uint32_t key_big(BigGeo const& b, PathF32 const& p, R
     float const cp = fmaf(r.o2x, b.gx, fmaf(r.o2y, b.gy, fmaf(r.o2z, b.gz, fmaf(b.k, r.oo, b.K)))); // c / 2R
     float const disc = fmaf(hb, hb, -(b.k * cp));
     float const m = add_root(fabsf(hb), disc);
-    uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u; // sign bit set when hb >= 0 (sigma = -1)
-    float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
+    float const cs = flip_unless_negative(cp, hb); // sigma = -1 when hb >= 0
     float const t1 = fmaf(cs, fast_rcp(m), -r.eps);
     uint32_t key;
     if constexpr(kBoth) {
-        float const ms = __uint_as_float(__float_as_uint(m) ^ flip);
+        float const ms = flip_unless_negative(m, hb);
         float const t2 = fmaf(ms, b.two_r, -r.eps);
         key = min(__float_as_uint(t1), __float_as_uint(t2));
     }
@@ -316,9 +324,7 @@ __device__ __forceinline__ uint32_t key_big_axis(float ga, float K, float k, Pat
 #endif
     float const disc = fmaf(hb, hb, -(k * cp));
     float const m = add_root(fabsf(hb), disc);
-    uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
-    float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
-    return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
+    return __float_as_uint(fmaf(flip_unless_negative(cp, hb), fast_rcp(m), -r.eps));
 }
 
 // Two near-only axis spheres that are mirror images of each other (the left / right and top / bottom walls of
@@ -345,10 +351,8 @@ __device__ __forceinline__ uint32_t key_big_pair(float ga, float K, float k, Pat
 #endif
     float const disc = fmaf(hb, hb, -(k * cp));
     float const m = add_root(fabsf(hb), disc);
-    uint32_t const flip = ~__float_as_uint(hb) & 0x80000000u;
-    float const cs = __uint_as_float(__float_as_uint(cp) ^ flip);
     sel = sign >> 31;
-    return __float_as_uint(fmaf(cs, fast_rcp(m), -r.eps));
+    return __float_as_uint(fmaf(flip_unless_negative(cp, hb), fast_rcp(m), -r.eps));
 }
 
 // ---- closest hit through the bounding-volume hierarchy (ptb_bvh.hpp) -------------
