@@ -13,6 +13,10 @@
 
 // build/ptb_jit_sources.inc (Makefile): kJitHeaderNames[], kJitHeaderSources[], kJitHeaderCount -- the device
 // headers as they were when the library was built
+#ifndef PTB_TOOLKIT_LIBDIR
+#define PTB_TOOLKIT_LIBDIR "/usr/local/cuda/lib64"
+#endif
+
 #include "ptb_jit_sources.inc"
 
 namespace ptb {
@@ -59,7 +63,14 @@ Api& api()
         if(off != nullptr && std::strcmp(off, "0") == 0) {
             return x;
         }
-        for(char const* n : { "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so" }) {
+        // Which NVRTC: PTB_NVRTC_LIB, else the one of the toolkit this library was built with (by PATH, so that it is that
+        // file even when the process already holds another libnvrtc.so.12 -- a Python process that imported torch has torch's
+        // bundled 12.8, whose code for this kernel measured 2.8 % slower than 12.9's), else whatever the name resolves to.
+        char const* const env_lib = std::getenv("PTB_NVRTC_LIB");
+        for(char const* n : { env_lib, PTB_TOOLKIT_LIBDIR "/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12" }) {
+            if(n == nullptr || *n == '\0') {
+                continue;
+            }
             x.nvrtc = dlopen(n, RTLD_NOW | RTLD_LOCAL);
             if(x.nvrtc != nullptr) {
                 break;
