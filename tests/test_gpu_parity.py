@@ -499,6 +499,42 @@ def test_rays_inside_large_spheres_take_the_exact_self_roots(gpu, oracle_port, w
     assert abs(st_jit.rays - st_pre.rays) <= 2e-3 * st_pre.rays, (label, jit_ran, st_jit.rays, st_pre.rays)
 
 
+def test_runtime_compilation_of_a_20_sphere_scene_that_is_large_against_epsilon(gpu, oracle_port):
+    """17 .. 32 spheres fit the unrolled scan only with full-precision keys (the index has 4 spare bits in the key): a scene
+    that spreads over tens of units takes that path, and its run-time build must compile -- it once tripped over a
+    static_assert meant for the index-in-key kernels only and fell back after a wasted compilation on every new scene."""
+    W, H, S = 96, 54, 6
+    rng = np.random.default_rng(20)
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    cam = gpu.camera_with_config(cfg)
+    sph = np.zeros(20, dtype=gpu.SPHERE_DTYPE)
+    sph["radius"] = rng.uniform(0.3, 1.2, 20)
+    sph["position"] = rng.uniform(-15.0, 15.0, (20, 3))
+    sph["position"][:, 2] -= 20.0
+    sph["color"] = rng.uniform(0.2, 0.9, (20, 3))
+    sph["emission"][::5] = 3.0
+    sph["reflection"] = rng.integers(0, 3, 20)
+    ref = oracle_port.render(sph, cam, W, H, S, 2, 9, 0)
+    flags = gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        if not r.jit_info()["available"]:
+            pytest.skip("run-time compilation not available")
+        lay = r.scene_layout()
+        assert lay["embed_ok"] == 0 and lay["fits_const"] == 1 and lay["specialised"] == 0
+        r.render(9, 0, S, flags | gpu.CODEGEN_PRECOMPILED)
+        pre, st_p = r.download_accum(), r.stats()
+        r.clear()
+        r.render(9, 0, S, flags)
+        r.clear()
+        r.render(9, 0, S, flags)
+        info = r.jit_info()
+        assert info["failures"] == 0 and info["last_launch_jit"] == 1, info["last_error"]
+        jit, st_j, img = r.download_accum(), r.stats(), r.resolve()
+    assert np.all(jit[:, 3] == S) and np.isfinite(jit).all()
+    assert abs(st_j.rays - st_p.rays) <= 2e-3 * st_p.rays
+    assert np.abs(img - ref).mean() < 2e-3
+
+
 @pytest.mark.parametrize("refl", [0, 1, 2])
 def test_runtime_compilation_of_a_one_sphere_scene(gpu, oracle_port, refl):
     """The smallest layouts (one small sphere, no big one; near-only or both-roots list alone)."""
