@@ -462,6 +462,8 @@ def main():
         }
         if parity_n is not None:
             line["parity_n"] = parity_n
+        if args.other_configs and world == 1 and not args.no_cpu_baseline:
+            line["image_rmse"] = image_rmse_c1(pkg, local)
         if others:
             line["other_configs"] = others
         if not args.no_cpu_baseline:
@@ -475,6 +477,38 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def image_rmse_c1(pkg, device):
+    """BASELINE.json configs[0] and the "image RMSE vs reference" half of the metric: simple_scene 1024x768 at 16 spp, the GPU
+    render (product path) against K = 4 renders of the reference's own OpenMP code (stock mt19937 seeded from random_device:
+    independent by construction) on this box's host cores.  Per channel: RMSE(GPU, mean of the K) against the Monte-Carlo
+    bound sqrt(mean per-pixel variance x (1 + 1/K)) estimated from the K renders themselves ('Image RMSE')."""
+    from oracle import Oracle, available
+
+    W, H, SPP, K = 1024, 768, 16, 4
+    cores = os.cpu_count() or 1
+    if available("ref_stock"):
+        orc, kind = Oracle("ref_stock"), "reference"
+        sph, _, cam = orc.scene("simple", W, H)
+        refs = np.stack([orc.mt_render(sph, cam, W, H, SPP // 4, 2, seed_mode=0, nthreads=cores) for _ in range(K)])
+    else:
+        orc, kind = Oracle("port"), "port"
+        sph, cfg = pkg.builtin_scene("simple", W, H)
+        cam = pkg.camera_with_config(cfg)
+        refs = np.stack([orc.render(sph, cam, W, H, SPP // 4, 2, 7000 + k, 0, nthreads=cores) for k in range(K)])
+    with pkg.Renderer(device) as r:
+        r.upload_scene(sph)
+        r.set_camera(cam)
+        r.set_image(W, H, 2)
+        r.render(SEED, 0, SPP // 4, pkg.PRECISION_FP32 | pkg.VARIANT_MEGAKERNEL_SORTED)
+        img = r.resolve()
+    mean_ref, var_px = refs.mean(axis=0), refs.var(axis=0, ddof=1)
+    rmse = [float(np.sqrt(np.mean((img[..., c] - mean_ref[..., c]) ** 2))) for c in range(3)]
+    bound = [float(np.sqrt(np.mean(var_px[..., c]) * (1.0 + 1.0 / K))) for c in range(3)]
+    ratio = [a / b for a, b in zip(rmse, bound)]
+    return {"workload": f"C1: simple {W}x{H} @ {SPP} spp (BASELINE.json configs[0])", "reference": kind, "k_reference_renders": K,
+            "rmse_rgb": rmse, "noise_bound_rgb": bound, "rmse_over_bound": ratio, "within_1p1_bound": bool(max(ratio) <= 1.1)}
 
 
 def ncu_counters(cfg_name, variant):
