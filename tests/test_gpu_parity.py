@@ -954,6 +954,30 @@ def test_full_size_frames(gpu, cfg_name, scene, W, H):
     assert abs(total - rows.sum()) <= 1e-9 * abs(total)
 
 
+@pytest.mark.parametrize("scene,W,H", [("box", 1024, 768), ("box_mirror", 1920, 1080), ("dof_glass", 3840, 2160)])
+def test_full_size_frames_fp32_against_the_fp64_kernel(gpu, scene, W, H):
+    """BASELINE resolutions, same seed: the FP32 product path against the FP64 deterministic kernel (itself pinned to the
+    oracle sample by sample).  Same uniforms, so the two images differ only by rounding and by the few chaotic paths:
+    per-pixel agreement at full frame size, not a statistic of a small frame."""
+    S = 2
+    sph, cfg = gpu.builtin_scene(scene, W, H)
+    cam = gpu.camera_with_config(cfg)
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        r.render(11, 0, S, gpu.PRECISION_FP64)
+        img64, st64 = r.resolve(), r.stats()
+        r.clear()
+        r.render(11, 0, S, gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED)
+        img32, st32 = r.resolve(), r.stats()
+    assert st32.paths == st64.paths == W * H * 4 * S
+    assert abs(st32.rays - st64.rays) <= 2e-3 * st64.rays
+    diff = np.abs(img32 - img64)
+    assert diff.mean() < 1e-3, diff.mean()
+    # 8 samples per pixel; a chaotic path moves its pixel, everything else agrees to FP32 rounding
+    assert (diff.max(axis=2) < 1e-4).mean() > (0.93 if scene == "box_mirror" else 0.97)
+    for c in range(3):
+        assert abs(img32[..., c].mean() - img64[..., c].mean()) < 2e-4
+
+
 def test_spheres10k_small_frame(gpu, oracle_port):
     """BASELINE config 5 geometry (10 001 spheres) on a small frame: the run-time-count kernel with geometry
     streamed from global memory."""
