@@ -1041,6 +1041,12 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
 
     // Scene-specialised code: compiled (once per scene, ~0.4 s) BEFORE the timed region starts.
     int sorted_inline = ctx->inline_material;
+    if(ctx->have_bvh && accel != PTB_ACCEL_SCAN) {
+        // Scenes behind the hierarchy scatter NOTHING in place: then every lane takes a new ray after every bounce, all 32
+        // from the top of READY -- the batch the camera or the scatter stage pushed last, rays of one kind that descend
+        // the tree alike (measured on config 5: -9.3 % time against diffuse in place, -7.4 % against mirror in place)
+        sorted_inline = -1;
+    }
     if(char const* force = std::getenv("PTB_INLINE_MATERIAL")) { // experiments (dev/)
         int const f = std::atoi(force);
         sorted_inline = f < 0 ? -1 : f == 0 ? 0 : 1;

@@ -484,6 +484,13 @@ cudaError_t launch_megakernel_sorted(RenderParamsF32 const& p, SceneCounts const
     if(launches != nullptr) {
         *launches += 1;
     }
+    if(inline_material < 0) {
+        // no material in place: every surviving hit is parked, so after a bounce ALL lanes take new rays and take them from
+        // the top of READY -- a batch the scatter stage or the camera just pushed, i.e. rays of one kind.  Precompiled for the
+        // run-time-count kernel only (scenes behind the hierarchy, where lanes of one kind descend alike)
+        return p.n_total <= kSmemShadeSpheres ? launch_sorted_one<GenericShape, true, -1>(p, sm_count, stream)
+                                              : launch_sorted_one<GenericShape, false, -1>(p, sm_count, stream);
+    }
     return inline_material == 0 ? launch_sorted_inline<0>(p, c, sm_count, stream) : launch_sorted_inline<1>(p, c, sm_count, stream);
 }
 

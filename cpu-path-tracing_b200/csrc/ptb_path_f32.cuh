@@ -556,9 +556,6 @@ __device__ __forceinline__ bool closest_hit(Scene const& cs, GeoLists const& gl,
     else {
         int const nsn = gl.bvh_nodes != nullptr ? 0 : cs.n_small_near, ns = cs.n_small;
         int const nbn = cs.n_big_near, nb = cs.n_big;
-        if(gl.bvh_nodes != nullptr) {
-            bvh_closest_hit(gl, p, r, best, id);
-        }
 #pragma unroll 4
         for(int i = 0; i < nsn; ++i) {
             uint32_t const k = key_small<false, true>(gl.small_geo[i], p, r, p.last == i);
@@ -587,6 +584,11 @@ __device__ __forceinline__ bool closest_hit(Scene const& cs, GeoLists const& gl,
                 best = k;
                 id = ns + i;
             }
+        }
+        // the hierarchy LAST: the few huge spheres (a ground, walls) have given an upper bound by now, and the traversal
+        // drops every box the ray enters beyond it.  Equal roots still go to the lower list position (the traversal's own rule).
+        if(gl.bvh_nodes != nullptr) {
+            bvh_closest_hit(gl, p, r, best, id);
         }
     }
     id_out = id;
