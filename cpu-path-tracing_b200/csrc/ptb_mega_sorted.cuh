@@ -248,21 +248,23 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     // material is the sphere's: read back from its shading plane rather than carried through the pool
                     float4 const sa = shade(0, last);
                     int const mat = __float_as_int(shade(1, last).w) & 0xff;
-                    float nx, ny, nz;
-                    unit_normal(q.ox, q.oy, q.oz, sa, nx, ny, nz);
-                    float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
-                    if(mat == 0) {
-                        cnt.diffuse++;
-                        bool const front = dn < 0.0f; // hit_record.cpp:7
-                        scatter_diffuse(q, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
-                    }
-                    else if(mat == 1) {
+                    if(mat == 1) {
                         cnt.specular++;
-                        reflect_ray(q, nx, ny, nz);
+                        mirror_at_hit(q, sa);
                     }
                     else {
-                        cnt.dielectric++;
-                        scatter_dielectric(q, nx, ny, nz, dn);
+                        float nx, ny, nz;
+                        unit_normal(q.ox, q.oy, q.oz, sa, nx, ny, nz);
+                        float const dn = fmaf(nx, q.dx, fmaf(ny, q.dy, nz * q.dz));
+                        if(mat == 0) {
+                            cnt.diffuse++;
+                            bool const front = dn < 0.0f; // hit_record.cpp:7
+                            scatter_diffuse(q, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);
+                        }
+                        else {
+                            cnt.dielectric++;
+                            scatter_dielectric(q, nx, ny, nz, dn);
+                        }
                     }
                     // the ray scattered by the last iteration is never traced (main.cpp:111): the path ends here
                     out = dl1 < (static_cast<uint32_t>(kDepthLimit) << 24);
@@ -386,13 +388,13 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 }
                 else if(((tag ^ kInline) & 0xff) == 0 && dl < (static_cast<uint32_t>(kDepthLimit - 1) << 24)) {
                     float4 const sa = shade(0, id);
-                    float nx, ny, nz; // outward unit normal, hit_record.cpp:6
-                    unit_normal(p.ox, p.oy, p.oz, sa, nx, ny, nz);
                     if constexpr(kInline == 1) {
                         cnt.specular++;
-                        reflect_ray(p, nx, ny, nz); // specular_ray, main.cpp:60-67
+                        mirror_at_hit(p, sa); // specular_ray, main.cpp:60-67
                     }
                     else {
+                        float nx, ny, nz; // outward unit normal, hit_record.cpp:6
+                        unit_normal(p.ox, p.oy, p.oz, sa, nx, ny, nz);
                         cnt.diffuse++;
                         bool const front = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz)) < 0.0f; // hit_record.cpp:7
                         scatter_diffuse(p, front ? nx : -nx, front ? ny : -ny, front ? nz : -nz);

@@ -488,7 +488,9 @@ template<class Shape, bool kKeepReg = false, class Scene = ConstSceneF32>
 __device__ __forceinline__ bool closest_hit(Scene const& cs, GeoLists const& gl, PathF32 const& p,
                                             RayTerms const& r, float& t_out, int& id_out, uint32_t keep_reg = 0u)
 {
-    uint32_t best = kNoHitBits;
+    // index-in-key scan: the running minimum starts ABOVE every key (a miss is any key >= +inf's bits), so that no
+    // "min(best, inf)" is needed before the position is taken out of the winner
+    uint32_t best = (!Shape::generic && Shape::embed) ? 0xFFFFFFFFu : kNoHitBits;
     int id = -1;
     if constexpr(!Shape::generic) {
         // only the index-in-key kernels are limited by the key's spare bits; full-precision keys carry the id separately
@@ -638,6 +640,22 @@ __device__ __forceinline__ void reflect_ray(PathF32& p, float nx, float ny, floa
     (void)rng_next32(p.rng);
 }
 
+// specular_ray for a ray that stands on its hit point (p.o = P): mirror about m = (P - c) / R WITHOUT normalising it --
+// r = d - 2 (m.d) / (m.m) m is the exact reflection whatever |m| is (so nothing feeds a deviation of |m| back into the
+// direction, the failure unit_normal guards against), and it costs a reciprocal and two products where the unit normal
+// costs a reciprocal square root and three.  Every FP32 variant mirrors through this one function.
+__device__ __forceinline__ void mirror_at_hit(PathF32& p, float4 const& sa)
+{
+    float const mx = fmaf(p.ox, sa.w, sa.x), my = fmaf(p.oy, sa.w, sa.y), mz = fmaf(p.oz, sa.w, sa.z);
+    float const mm = fmaf(mx, mx, fmaf(my, my, mz * mz));
+    float const md = fmaf(mx, p.dx, fmaf(my, p.dy, mz * p.dz));
+    float const sc = -2.0f * md * fast_rcp(mm);
+    p.dx = fmaf(sc, mx, p.dx);
+    p.dy = fmaf(sc, my, p.dy);
+    p.dz = fmaf(sc, mz, p.dz);
+    (void)rng_next32(p.rng); // the dead "fuzz" draw of main.cpp:65
+}
+
 // ---- one iteration of the bounce loop of main.cpp:111-155 AFTER the closest-hit query ----------
 // Split in two so that the wavefront variant can run the halves in different kernels:
 //   shade_common : sky on a miss, hit record, emission, Russian roulette, throughput
@@ -778,7 +796,7 @@ __device__ __forceinline__ bool shade_bounce(PathF32& p, bool hit, float t, int 
         if(kCount) {
             cnt.specular++;
         }
-        reflect_ray(p, nx, ny, nz);
+        mirror_at_hit(p, sp.a[id]);
     }
     else {
         float const dn = fmaf(nx, p.dx, fmaf(ny, p.dy, nz * p.dz));

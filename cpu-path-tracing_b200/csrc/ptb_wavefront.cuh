@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kWfThreads) wf_extend_kernel(WavefrontState co
             if(alive) {
                 if(refl == 1) {
                     nsp++;
-                    reflect_ray(p, nx, ny, nz); // specular_ray, main.cpp:60-67
+                    mirror_at_hit(p, sp.a[id]); // specular_ray, main.cpp:60-67
                     p.depth++;
                     alive = p.depth < kDepthLimit; // main.cpp:111
                     dest = 0;
