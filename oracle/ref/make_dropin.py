@@ -59,8 +59,17 @@ def patch(text: str) -> str:
 SANDBOX_BLOCK = '''    Vec* c = new Vec[w * h];
     static_assert(sizeof(Sphere) == PTB_SPHERE_BYTES && sizeof(Vec) == 3 * sizeof(double), "the program's own records cross the boundary");
     double const cam8[8] = { cam.o.x, cam.o.y, cam.o.z, cam.d.x, cam.d.y, cam.d.z, .5135, 140 };
+    int devices[16]; // every GPU of the machine, as the OpenMP loop used every core; PTB_GPUS=n caps it
+    int n_gpus = ptb_device_count() < 16 ? ptb_device_count() : 16;
+    if(char const* cap = getenv("PTB_GPUS")) {
+        n_gpus = atoi(cap) < n_gpus ? atoi(cap) : n_gpus;
+    }
+    n_gpus = n_gpus < 1 ? 1 : n_gpus; // none: let the library say so
+    for(int i = 0; i < n_gpus; ++i) {
+        devices[i] = i;
+    }
     ptb_context* gpu = nullptr;
-    if(ptb_create(/*device*/ 0, &gpu) != PTB_OK) {
+    if(ptb_create_multi(devices, n_gpus, &gpu) != PTB_OK) {
         fprintf(stderr, "%s\\n", ptb_last_error(nullptr));
         return 1;
     }

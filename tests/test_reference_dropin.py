@@ -102,8 +102,8 @@ needs_sb = pytest.mark.skipif(not os.path.exists(SB_EXE), reason="oracle/_ref/sm
 def test_sandbox_program_binds_only_the_abi():
     und = subprocess.run(["nm", "-D", "--undefined-only", SB_EXE], capture_output=True, text=True, check=True).stdout
     bound = sorted(l.split()[-1] for l in und.splitlines() if " ptb_" in l)
-    assert bound == ["ptb_create", "ptb_destroy", "ptb_last_error", "ptb_render", "ptb_resolve", "ptb_set_image",
-                     "ptb_set_smallpt_camera", "ptb_upload_scene"]
+    assert bound == ["ptb_create_multi", "ptb_destroy", "ptb_device_count", "ptb_last_error", "ptb_render", "ptb_resolve",
+                     "ptb_set_image", "ptb_set_smallpt_camera", "ptb_upload_scene"]
     # the program's own radiance() is still compiled (dead code now, hence erand48), its thread pool is gone
     assert "omp_" not in und and "GOMP" not in und
 
