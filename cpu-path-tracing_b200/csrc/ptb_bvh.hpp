@@ -9,8 +9,10 @@
 //
 // Layout (device, ptb_scene.cuh: GeoLists): binary tree, 64-byte nodes that hold the boxes of BOTH
 // children so that one node fetch (4 x 16 bytes) decides where to go:
-//   n0 = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)      n1 = the same for child 1
-//   n2 = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)      n3 = (child0, child1, -, -) as int bits
+//   n0 = (c0.mid.x, c0.half.x, c0.mid.y, c0.half.y)    n1 = the same for child 1
+//   n2 = (c0.mid.z, c0.half.z, c1.mid.z, c1.half.z)    n3 = (child0, child1, -, -) as int bits
+// each slab as (centre, half width) -- the half width rounded up, so the pair still encloses the padded box: entry and
+// exit distances are then two FFMAs off the centre's distance, with no per-axis min / max (ptb_path_f32.cuh: bvh_closest_hit).
 // child >= 0: index of an inner node; child < 0: leaf, ~child = first * 8 + (count - 1) into the
 // leaf-ordered sphere arrays (count <= 8).  Built top-down with a 16-bin surface-area heuristic.
 #pragma once
@@ -214,18 +216,21 @@ struct Builder
         int32_t const c0 = build(b, mid, lb, depth + 1);
         int32_t const c1 = build(mid, e, rb, depth + 1);
         BvhNode64& nd = tree.nodes[static_cast<size_t>(me)];
-        nd.n0[0] = lb.lo[0];
-        nd.n0[1] = lb.hi[0];
-        nd.n0[2] = lb.lo[1];
-        nd.n0[3] = lb.hi[1];
-        nd.n1[0] = rb.lo[0];
-        nd.n1[1] = rb.hi[0];
-        nd.n1[2] = rb.lo[1];
-        nd.n1[3] = rb.hi[1];
-        nd.n2[0] = lb.lo[2];
-        nd.n2[1] = lb.hi[2];
-        nd.n2[2] = rb.lo[2];
-        nd.n2[3] = rb.hi[2];
+        // each slab as (centre, half width), the half width rounded UP so that the float pair still encloses [lo, hi]
+        auto const slab = [](float lo, float hi, float& c, float& h) {
+            c = static_cast<float>(0.5 * (static_cast<double>(lo) + static_cast<double>(hi)));
+            double const need = std::max(static_cast<double>(hi) - static_cast<double>(c), static_cast<double>(c) - static_cast<double>(lo));
+            h = static_cast<float>(need);
+            if(static_cast<double>(h) < need) {
+                h = std::nextafter(h, std::numeric_limits<float>::infinity());
+            }
+        };
+        slab(lb.lo[0], lb.hi[0], nd.n0[0], nd.n0[1]);
+        slab(lb.lo[1], lb.hi[1], nd.n0[2], nd.n0[3]);
+        slab(rb.lo[0], rb.hi[0], nd.n1[0], nd.n1[1]);
+        slab(rb.lo[1], rb.hi[1], nd.n1[2], nd.n1[3]);
+        slab(lb.lo[2], lb.hi[2], nd.n2[0], nd.n2[1]);
+        slab(rb.lo[2], rb.hi[2], nd.n2[2], nd.n2[3]);
         nd.child[0] = c0;
         nd.child[1] = c1;
         nd.child[2] = nd.child[3] = 0;

@@ -363,13 +363,16 @@ __device__ __forceinline__ uint32_t key_big_pair(float ga, float K, float k, Pat
 __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 const& p, RayTerms const& r, uint32_t& best,
                                                 int& id)
 {
-    // slab test t = plane * (1/d) - o * (1/d), one FFMA per plane.  Against (plane - o) * (1/d) the rounding of o * (1/d)
-    // moves t by up to 6e-8 |o| in space units -- the boxes are padded by 1e-6 |c| + 1e-5 for exactly that (ptb_bvh.hpp).
+    // slab test: t_mid = mid * (1/d) - o * (1/d), entry / exit = t_mid -+ half * |1/d| -- three FFMAs per slab and NO min / max
+    // to order the two planes (FMNMX issues at half rate, on the pipe this loop loads most: -3.7 % time on config 5 against
+    // one FFMA per plane + min + max).  Against (plane - o) * (1/d) the roundings move t by up to ~1e-7 (|o| + |mid|) in
+    // space units -- the boxes are padded by 1e-6 |c| + 1e-5 for exactly that (ptb_bvh.hpp).
     // A zero direction component must not become inf (inf - inf): |d_a| is floored at 1e-20, which keeps both plane
     // distances finite and of the right signs (+-1e20 scale: "never reached" or "always inside").
     auto const safe_rcp = [](float d) { return fast_rcp(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); };
     float const ix = safe_rcp(p.dx), iy = safe_rcp(p.dy), iz = safe_rcp(p.dz);
     float const nx = -p.ox * ix, ny = -p.oy * iy, nz = -p.oz * iz;
+    float const jx = fabsf(ix), jy = fabsf(iy), jz = fabsf(iz);
     float tbest = best < kNoHitBits ? __uint_as_float(best) + r.eps : 3.0e38f;
     int stack[kBvhStack];
     int sp = 0;
@@ -380,16 +383,12 @@ __device__ __forceinline__ void bvh_closest_hit(GeoLists const& gl, PathF32 cons
             float4 const n1 = gl.bvh_nodes[4 * node + 1];
             float4 const n2 = gl.bvh_nodes[4 * node + 2];
             float4 const n3 = gl.bvh_nodes[4 * node + 3];
-            float const ax0 = fmaf(n0.x, ix, nx), ax1 = fmaf(n0.y, ix, nx);
-            float const ay0 = fmaf(n0.z, iy, ny), ay1 = fmaf(n0.w, iy, ny);
-            float const az0 = fmaf(n2.x, iz, nz), az1 = fmaf(n2.y, iz, nz);
-            float const bx0 = fmaf(n1.x, ix, nx), bx1 = fmaf(n1.y, ix, nx);
-            float const by0 = fmaf(n1.z, iy, ny), by1 = fmaf(n1.w, iy, ny);
-            float const bz0 = fmaf(n2.z, iz, nz), bz1 = fmaf(n2.w, iz, nz);
-            float const amin = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
-            float const amax = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tbest));
-            float const bmin = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
-            float const bmax = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), tbest));
+            float const acx = fmaf(n0.x, ix, nx), acy = fmaf(n0.z, iy, ny), acz = fmaf(n2.x, iz, nz);
+            float const bcx = fmaf(n1.x, ix, nx), bcy = fmaf(n1.z, iy, ny), bcz = fmaf(n2.z, iz, nz);
+            float const amin = fmaxf(fmaxf(fmaf(-n0.y, jx, acx), fmaf(-n0.w, jy, acy)), fmaxf(fmaf(-n2.y, jz, acz), 0.0f));
+            float const amax = fminf(fminf(fmaf(n0.y, jx, acx), fmaf(n0.w, jy, acy)), fminf(fmaf(n2.y, jz, acz), tbest));
+            float const bmin = fmaxf(fmaxf(fmaf(-n1.y, jx, bcx), fmaf(-n1.w, jy, bcy)), fmaxf(fmaf(-n2.w, jz, bcz), 0.0f));
+            float const bmax = fminf(fminf(fmaf(n1.y, jx, bcx), fmaf(n1.w, jy, bcy)), fminf(fmaf(n2.w, jz, bcz), tbest));
             bool const ha = amin <= amax, hb = bmin <= bmax;
             int const ca = __float_as_int(n3.x), cb = __float_as_int(n3.y);
             if(ha && hb) {

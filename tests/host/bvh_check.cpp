@@ -1,5 +1,5 @@
 // Host-side check of the bounding-volume hierarchy builder (cpu-path-tracing_b200/csrc/ptb_bvh.hpp):
-//   1. structure: every sphere sits in exactly one leaf, every child box encloses its spheres' padded boxes;
+//   1. structure: every sphere sits in exactly one leaf, every child box (stored as centre + half width per slab) encloses its spheres;
 //   2. queries: a CPU restatement of the device traversal (ptb_path_f32.cuh: bvh_closest_hit, binary32, same
 //      operation order) returns exactly the (root, sphere) pair of a linear scan with the same sphere test,
 //      for rays from outside, from inside the cloud and from sphere surfaces.
@@ -68,7 +68,8 @@ void traverse(std::vector<BvhSphere> const& s, BvhTree const& t, Ray const& r, u
     id = -1;
     auto const safe_rcp = [](float d) { return 1.0f / (std::fabs(d) > 1e-20f ? d : std::copysign(1e-20f, d)); };
     float const ix = safe_rcp(r.dx), iy = safe_rcp(r.dy), iz = safe_rcp(r.dz);
-    float const nx = -r.ox * ix, ny = -r.oy * iy, nz = -r.oz * iz; // t = plane * (1/d) - o * (1/d), as on the device
+    float const nx = -r.ox * ix, ny = -r.oy * iy, nz = -r.oz * iz; // t_mid = mid * (1/d) - o * (1/d), as on the device
+    float const jx = std::fabs(ix), jy = std::fabs(iy), jz = std::fabs(iz); // entry / exit = t_mid -+ half * |1/d|
     float tbest = 3.0e38f;
     int stack[64];
     int sp = 0;
@@ -77,16 +78,12 @@ void traverse(std::vector<BvhSphere> const& s, BvhTree const& t, Ray const& r, u
         if(node >= 0) {
             ++g_nodes;
             ptb::BvhNode64 const& n = t.nodes[static_cast<size_t>(node)];
-            float const ax0 = std::fmaf(n.n0[0], ix, nx), ax1 = std::fmaf(n.n0[1], ix, nx);
-            float const ay0 = std::fmaf(n.n0[2], iy, ny), ay1 = std::fmaf(n.n0[3], iy, ny);
-            float const az0 = std::fmaf(n.n2[0], iz, nz), az1 = std::fmaf(n.n2[1], iz, nz);
-            float const bx0 = std::fmaf(n.n1[0], ix, nx), bx1 = std::fmaf(n.n1[1], ix, nx);
-            float const by0 = std::fmaf(n.n1[2], iy, ny), by1 = std::fmaf(n.n1[3], iy, ny);
-            float const bz0 = std::fmaf(n.n2[2], iz, nz), bz1 = std::fmaf(n.n2[3], iz, nz);
-            float const amin = std::fmax(std::fmax(std::fmin(ax0, ax1), std::fmin(ay0, ay1)), std::fmax(std::fmin(az0, az1), 0.0f));
-            float const amax = std::fmin(std::fmin(std::fmax(ax0, ax1), std::fmax(ay0, ay1)), std::fmin(std::fmax(az0, az1), tbest));
-            float const bmin = std::fmax(std::fmax(std::fmin(bx0, bx1), std::fmin(by0, by1)), std::fmax(std::fmin(bz0, bz1), 0.0f));
-            float const bmax = std::fmin(std::fmin(std::fmax(bx0, bx1), std::fmax(by0, by1)), std::fmin(std::fmax(bz0, bz1), tbest));
+            float const acx = std::fmaf(n.n0[0], ix, nx), acy = std::fmaf(n.n0[2], iy, ny), acz = std::fmaf(n.n2[0], iz, nz);
+            float const bcx = std::fmaf(n.n1[0], ix, nx), bcy = std::fmaf(n.n1[2], iy, ny), bcz = std::fmaf(n.n2[2], iz, nz);
+            float const amin = std::fmax(std::fmax(std::fmaf(-n.n0[1], jx, acx), std::fmaf(-n.n0[3], jy, acy)), std::fmax(std::fmaf(-n.n2[1], jz, acz), 0.0f));
+            float const amax = std::fmin(std::fmin(std::fmaf(n.n0[1], jx, acx), std::fmaf(n.n0[3], jy, acy)), std::fmin(std::fmaf(n.n2[1], jz, acz), tbest));
+            float const bmin = std::fmax(std::fmax(std::fmaf(-n.n1[1], jx, bcx), std::fmaf(-n.n1[3], jy, bcy)), std::fmax(std::fmaf(-n.n2[3], jz, bcz), 0.0f));
+            float const bmax = std::fmin(std::fmin(std::fmaf(n.n1[1], jx, bcx), std::fmaf(n.n1[3], jy, bcy)), std::fmin(std::fmaf(n.n2[3], jz, bcz), tbest));
             bool const ha = amin <= amax, hb = bmin <= bmax;
             int const ca = n.child[0], cb = n.child[1];
             if(ha && hb) {
@@ -134,6 +131,46 @@ int check(std::vector<BvhSphere> const& s, int nrays, unsigned seed, char const*
             std::printf("FAIL %s: sphere %zu appears %d times in the leaves\n", what, i, seen[i]);
             return 1;
         }
+    }
+    // every child's slabs (centre -+ half width, taken exactly) enclose every sphere below that child
+    struct Bounds
+    {
+        double lo[3], hi[3];
+    };
+    bool enclosed = true;
+    auto const below = [&](auto const& self, int code) -> Bounds {
+        Bounds b{ { 1e300, 1e300, 1e300 }, { -1e300, -1e300, -1e300 } };
+        auto const grow = [&](Bounds const& o) {
+            for(int a = 0; a < 3; ++a) {
+                b.lo[a] = std::min(b.lo[a], o.lo[a]);
+                b.hi[a] = std::max(b.hi[a], o.hi[a]);
+            }
+        };
+        if(code < 0) {
+            int const first = (~code) >> 3, count = ((~code) & 7) + 1;
+            for(int k = 0; k < count; ++k) {
+                BvhSphere const& sp = s[static_cast<size_t>(t.leaf_order[static_cast<size_t>(first + k)])];
+                double const c[3] = { sp.cx, sp.cy, sp.cz }, r = std::fabs(static_cast<double>(sp.r));
+                grow(Bounds{ { c[0] - r, c[1] - r, c[2] - r }, { c[0] + r, c[1] + r, c[2] + r } });
+            }
+            return b;
+        }
+        ptb::BvhNode64 const& n = t.nodes[static_cast<size_t>(code)];
+        double const mid[2][3] = { { n.n0[0], n.n0[2], n.n2[0] }, { n.n1[0], n.n1[2], n.n2[2] } };
+        double const half[2][3] = { { n.n0[1], n.n0[3], n.n2[1] }, { n.n1[1], n.n1[3], n.n2[3] } };
+        for(int c = 0; c < 2; ++c) {
+            Bounds const sub = self(self, n.child[c]);
+            for(int a = 0; a < 3; ++a) {
+                enclosed = enclosed && mid[c][a] - half[c][a] <= sub.lo[a] && sub.hi[a] <= mid[c][a] + half[c][a];
+            }
+            grow(sub);
+        }
+        return b;
+    };
+    below(below, t.root);
+    if(!enclosed) {
+        std::printf("FAIL %s: a child's slabs do not enclose its spheres\n", what);
+        return 1;
     }
     if(t.max_depth > 64) {
         std::printf("FAIL %s: depth %d\n", what, t.max_depth);
