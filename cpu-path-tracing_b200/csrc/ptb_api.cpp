@@ -780,8 +780,9 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
     }
     PTB_GROUP(ctx, multi_upload_scene(ctx, spheres, count, stride));
     // count == 0 is a scene: every ray misses and sees the sky (main.cpp:114-120), spheres may then be null
-    if((spheres == nullptr && count != 0) || stride < PTB_SPHERE_BYTES || count > (1u << 24)) {
-        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need spheres of stride >= 88 bytes (at most 2^24)");
+    if((spheres == nullptr && count != 0) || stride < PTB_SPHERE_BYTES || count >= (1u << 24)) {
+        // list positions travel in 24 bits next to the path's depth, and 0xFFFFFF means "starts on no sphere" (ptb_mega_sorted.cuh: kNoSphere)
+        return fail(ctx, PTB_ERR_ARGUMENT, "ptb_upload_scene: need spheres of stride >= 88 bytes (fewer than 2^24 of them)");
     }
     PTB_CUDA(ctx, cudaSetDevice(ctx->device));
     // from here until everything derived from the new list is on the device there is NO usable scene: a CUDA failure

@@ -119,6 +119,7 @@ int ptb_synchronize(ptb_context* ctx);
 /* The sphere list of pt::scene (src/scene.hpp:12-16), in index order (the
  * closest-hit tie rule of src/main.cpp:35 depends on it).  `stride` >= 88.
  * count == 0 is valid (an empty pt::scene: every ray sees the sky, main.cpp:114-120).
+ * count < 2^24 (PTB_ERR_ARGUMENT otherwise: list positions travel in 24 bits of the path state).
  * Every number must be finite (PTB_ERR_ARGUMENT otherwise); a radius of 0 is a
  * sphere no ray hits, a negative radius counts as its magnitude (the reference
  * only squares it, src/sphere.cpp:11).

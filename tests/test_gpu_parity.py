@@ -897,6 +897,9 @@ def test_error_behaviour(gpu):
             with pytest.raises(gpu.PtbError) as e:
                 r.upload_scene(bad)
             assert e.value.code == -1 and "non-finite" in str(e.value)
+        # 2^24 spheres: refused before a byte is read (list positions travel in 24 bits, all ones = "no sphere")
+        assert gpu._ptb_upload_scene(r._ctx, sph.ctypes.data, 1 << 24, sph.dtype.itemsize) == -1
+        assert "2^24" in gpu._ptb_last_error(r._ctx).decode()
         r.upload_scene(sph)
         with pytest.raises(gpu.PtbError) as e:
             r.set_camera(np.zeros(10))
