@@ -611,6 +611,33 @@ int api_fail_cuda(ptb_context* ctx, cudaError_t e, char const* what)
 {
     return fail_cuda(ctx, e, what);
 }
+int api_exception(ptb_context* ctx, char const* entry) noexcept
+{
+    // called from a catch(...) handler: rethrow to learn what it was
+    char const* what = "unknown C++ exception";
+    int code = PTB_ERR_INTERNAL;
+    char buffer[256];
+    try {
+        throw;
+    }
+    catch(std::bad_alloc const&) {
+        what = "out of host memory";
+        code = PTB_ERR_MEMORY;
+    }
+    catch(std::exception const& e) {
+        std::snprintf(buffer, sizeof buffer, "%s", e.what());
+        what = buffer;
+    }
+    catch(...) {
+    }
+    try {
+        std::string& err = ctx != nullptr ? ctx->err : g_create_error;
+        err = std::string(entry) + ": " + what;
+    }
+    catch(...) { // no memory for the message either: the code still says what happened
+    }
+    return code;
+}
 } // namespace ptb
 
 // A handle made by ptb_create_multi stands for several member contexts: the call is theirs (ptb_multi.cpp)
@@ -624,7 +651,7 @@ int api_fail_cuda(ptb_context* ctx, cudaError_t e, char const* what)
 extern "C" {
 
 int ptb_device_count(void)
-{
+try {
     int n = 0;
     if(cudaGetDeviceCount(&n) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -632,6 +659,7 @@ int ptb_device_count(void)
     }
     return n;
 }
+PTB_CATCH(nullptr, "ptb_device_count")
 
 char const* ptb_last_error(ptb_context const* ctx)
 {
@@ -639,7 +667,7 @@ char const* ptb_last_error(ptb_context const* ctx)
 }
 
 int ptb_create(int device, ptb_context** out)
-{
+try {
     if(out == nullptr) {
         g_create_error = "ptb_create: out is null";
         return PTB_ERR_ARGUMENT;
@@ -688,6 +716,7 @@ int ptb_create(int device, ptb_context** out)
     *out = ctx;
     return PTB_OK;
 }
+PTB_CATCH(nullptr, "ptb_create")
 
 void ptb_destroy(ptb_context* ctx)
 {
@@ -735,7 +764,7 @@ void ptb_destroy(ptb_context* ctx)
 }
 
 int ptb_set_stream(ptb_context* ctx, void* cuda_stream)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -747,9 +776,10 @@ int ptb_set_stream(ptb_context* ctx, void* cuda_stream)
     ctx->stream = static_cast<cudaStream_t>(cuda_stream); // nullptr == the legacy default stream
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_set_stream")
 
 int ptb_reset_stream(ptb_context* ctx)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -761,9 +791,10 @@ int ptb_reset_stream(ptb_context* ctx)
     ctx->stream = ctx->own_stream;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_reset_stream")
 
 int ptb_synchronize(ptb_context* ctx)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -772,9 +803,10 @@ int ptb_synchronize(ptb_context* ctx)
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_synchronize")
 
 int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t stride)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -836,9 +868,10 @@ int ptb_upload_scene(ptb_context* ctx, void const* spheres, size_t count, size_t
     ctx->have_scene = rc == PTB_OK;
     return rc;
 }
+PTB_CATCH(ctx, "ptb_upload_scene")
 
 int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -865,9 +898,10 @@ int ptb_set_camera(ptb_context* ctx, void const* camera, size_t bytes)
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_set_camera")
 
 int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -892,9 +926,10 @@ int ptb_set_smallpt_camera(ptb_context* ctx, double const* cam8)
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_set_smallpt_camera")
 
 int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -950,9 +985,10 @@ int ptb_set_image(ptb_context* ctx, int width, int height, int num_subpixels)
     pack_camera(ctx);
     return ptb_clear(ctx);
 }
+PTB_CATCH(ctx, "ptb_set_image")
 
 int ptb_clear(ptb_context* ctx)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -973,9 +1009,10 @@ int ptb_clear(ptb_context* ctx)
     ctx->stats.kernel_launches = launches;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_clear")
 
 int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t samples_per_subpixel, uint32_t flags)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1182,6 +1219,7 @@ int ptb_render(ptb_context* ctx, uint64_t seed, uint32_t first_sample, uint32_t 
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_render")
 
 static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
 {
@@ -1223,17 +1261,19 @@ static int resolve_common(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out)
 }
 
 int ptb_resolve(ptb_context* ctx, double* rgb_out)
-{
+try {
     return resolve_common(ctx, rgb_out, nullptr);
 }
+PTB_CATCH(ctx, "ptb_resolve")
 
 int ptb_resolve_rgb8(ptb_context* ctx, uint8_t* rgb8_out)
-{
+try {
     return resolve_common(ctx, nullptr, rgb8_out);
 }
+PTB_CATCH(ctx, "ptb_resolve_rgb8")
 
 int ptb_resolve_device(ptb_context* ctx, void** device_rgb)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1259,9 +1299,10 @@ int ptb_resolve_device(ptb_context* ctx, void** device_rgb)
     *device_rgb = ctx->d_rgb;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_resolve_device")
 
 int ptb_measure_fp32_peak(ptb_context* ctx, double* tflops_out)
-{
+try {
     if(ctx == nullptr || tflops_out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1300,9 +1341,10 @@ int ptb_measure_fp32_peak(ptb_context* ctx, double* tflops_out)
     *tflops_out = flop / (best_ms * 1e-3) * 1e-12;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_measure_fp32_peak")
 
 int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes)
-{
+try {
     if(ctx == nullptr || device_ptr == nullptr || bytes == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1316,9 +1358,10 @@ int ptb_accum_buffer(ptb_context* ctx, void** device_ptr, size_t* bytes)
     *bytes = ctx->nslots * sizeof(float4);
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_accum_buffer")
 
 int ptb_set_accum_buffer(ptb_context* ctx, void* device_ptr, size_t bytes)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1340,9 +1383,10 @@ int ptb_set_accum_buffer(ptb_context* ctx, void* device_ptr, size_t bytes)
     ctx->ext_accum_bytes = bytes;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_set_accum_buffer")
 
 int ptb_download_accum(ptb_context* ctx, float* out, size_t floats)
-{
+try {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1358,10 +1402,11 @@ int ptb_download_accum(ptb_context* ctx, float* out, size_t floats)
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_download_accum")
 
 // ---- checkpoint / resume (include/ptb200.h; the reference's TODO, README.md:9) -------------------------------------
 int ptb_upload_accum(ptb_context* ctx, float const* in, size_t floats)
-{
+try {
     if(ctx == nullptr || in == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1377,9 +1422,10 @@ int ptb_upload_accum(ptb_context* ctx, float const* in, size_t floats)
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_upload_accum")
 
 int ptb_download_accum64(ptb_context* ctx, double* out, size_t doubles)
-{
+try {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1399,9 +1445,10 @@ int ptb_download_accum64(ptb_context* ctx, double* out, size_t doubles)
     PTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_download_accum64")
 
 int ptb_upload_accum64(ptb_context* ctx, double const* in, size_t doubles)
-{
+try {
     if(ctx == nullptr || in == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1422,9 +1469,10 @@ int ptb_upload_accum64(ptb_context* ctx, double const* in, size_t doubles)
     ctx->accum64_used = true;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_upload_accum64")
 
 int ptb_get_stats(ptb_context* ctx, ptb_stats* out)
-{
+try {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1440,9 +1488,10 @@ int ptb_get_stats(ptb_context* ctx, ptb_stats* out)
     *out = ctx->stats;
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_get_stats")
 
 int ptb_scene_layout(ptb_context* ctx, int32_t out[10])
-{
+try {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1457,9 +1506,10 @@ int ptb_scene_layout(ptb_context* ctx, int32_t out[10])
     std::memcpy(out, v, sizeof(v));
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_scene_layout")
 
 int ptb_jit_info(ptb_context* ctx, int32_t out[5])
-{
+try {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1471,6 +1521,7 @@ int ptb_jit_info(ptb_context* ctx, int32_t out[5])
     out[4] = static_cast<int32_t>(ctx->jit.compile_ms());
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_jit_info")
 
 char const* ptb_jit_last_error(ptb_context* ctx)
 {
@@ -1483,7 +1534,7 @@ char const* ptb_jit_last_error(ptb_context* ctx)
 int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,
                       uint32_t const* sy, uint32_t const* sample, size_t count, uint32_t flags, int32_t* primary_hit_out,
                       double* radiance_out, double* ray_out, uint32_t* draws_out)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1609,10 +1660,11 @@ int ptb_trace_samples(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32
 #undef PTB_CUDA_T
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_trace_samples")
 
 int ptb_trace_paths(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t const* y, uint32_t const* sx,
                     uint32_t const* sy, uint32_t const* sample, size_t count, int trail_len, int32_t* trail_out)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1670,10 +1722,11 @@ int ptb_trace_paths(ptb_context* ctx, uint64_t seed, uint32_t const* x, uint32_t
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_trace_paths")
 
 int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_t const* sample, size_t count,
                   int n_draws, double* draws_out)
-{
+try {
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1713,5 +1766,6 @@ int ptb_rng_draws(ptb_context* ctx, uint64_t seed, uint32_t const* slot, uint32_
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_rng_draws")
 
 } // extern "C"

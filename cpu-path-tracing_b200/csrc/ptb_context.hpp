@@ -113,6 +113,16 @@ int comm_resolve(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out, void** de
 int api_zero_accum(ptb_context* ctx); // accumulation buffers only: statistics and counters stay
 float4* api_active_accum(ptb_context* ctx);
 int api_fail(ptb_context* ctx, int code, char const* what);
+// What every `extern "C"` entry point does with a C++ exception (std::bad_alloc from a huge upload, std::system_error from
+// a thread that cannot start, ...): nothing may unwind into a caller that is C, Go or ctypes.  `ctx` may be null.
+int api_exception(ptb_context* ctx, char const* entry) noexcept;
 int api_fail_cuda(ptb_context* ctx, cudaError_t e, char const* what);
 
 } // namespace ptb
+
+// Function-try-block tail of an entry point returning a status: `int ptb_x(...) try { ... } PTB_CATCH(ctx, "ptb_x")`
+#define PTB_CATCH(ctx, entry) \
+    catch(...) \
+    { \
+        return ptb::api_exception((ctx), (entry)); \
+    }

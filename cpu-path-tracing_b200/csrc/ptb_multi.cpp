@@ -881,16 +881,17 @@ int comm_resolve(ptb_context* ctx, double* rgb_out, uint8_t* rgb8_out, void** de
 extern "C" {
 
 int ptb_sample_share(uint32_t total, int n_ranks, int rank, uint32_t* first_out, uint32_t* count_out)
-{
+try {
     if(n_ranks < 1 || rank < 0 || rank >= n_ranks || first_out == nullptr || count_out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
     ptb::share_of(total, n_ranks, rank, *first_out, *count_out);
     return PTB_OK;
 }
+PTB_CATCH(nullptr, "ptb_sample_share")
 
 int ptb_create_multi(int const* devices, int n_devices, ptb_context** out)
-{
+try {
     if(out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -946,9 +947,10 @@ int ptb_create_multi(int const* devices, int n_devices, ptb_context** out)
     *out = handle;
     return PTB_OK;
 }
+PTB_CATCH(nullptr, "ptb_create_multi")
 
 int ptb_comm_unique_id(void* id_out)
-{
+try {
     if(id_out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -962,9 +964,10 @@ int ptb_comm_unique_id(void* id_out)
     std::memcpy(id_out, &id, sizeof(id));
     return PTB_OK;
 }
+PTB_CATCH(nullptr, "ptb_comm_unique_id")
 
 int ptb_comm_init_rank(ptb_context* ctx, void const* id, int n_ranks, int rank)
-{
+try {
     using namespace ptb;
     if(ctx == nullptr) {
         return PTB_ERR_ARGUMENT;
@@ -1008,9 +1011,10 @@ int ptb_comm_init_rank(ptb_context* ctx, void const* id, int n_ranks, int rank)
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_comm_init_rank")
 
 int ptb_comm_set_transport(ptb_context* ctx, int transport)
-{
+try {
     if(ctx == nullptr || transport < PTB_TRANSPORT_AUTO || transport > PTB_TRANSPORT_PEER) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1025,9 +1029,10 @@ int ptb_comm_set_transport(ptb_context* ctx, int transport)
     }
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_comm_set_transport")
 
 int ptb_comm_info(ptb_context* ctx, int32_t out[6])
-{
+try {
     if(ctx == nullptr || out == nullptr) {
         return PTB_ERR_ARGUMENT;
     }
@@ -1050,5 +1055,6 @@ int ptb_comm_info(ptb_context* ctx, int32_t out[6])
     std::memcpy(out, v, sizeof(v));
     return PTB_OK;
 }
+PTB_CATCH(ctx, "ptb_comm_info")
 
 } // extern "C"

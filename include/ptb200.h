@@ -48,7 +48,9 @@ typedef enum ptb_status
     PTB_ERR_NO_DEVICE = -2, /* no CUDA device / device index out of range */
     PTB_ERR_CUDA = -3,      /* a CUDA runtime call failed; see ptb_last_error */
     PTB_ERR_STATE = -4,     /* call order: scene / camera / image not set yet */
-    PTB_ERR_IO = -5         /* file output failed */
+    PTB_ERR_IO = -5,        /* file output failed */
+    PTB_ERR_MEMORY = -6,    /* host memory exhausted (std::bad_alloc inside the library; nothing unwinds into the caller) */
+    PTB_ERR_INTERNAL = -7   /* any other C++ exception inside the library; see ptb_last_error */
 } ptb_status;
 
 /* ptb_render flags */

@@ -60,6 +60,18 @@ def test_product_never_imports_the_oracle():
                 assert "pt_oracle" not in code and "libptref" not in code and "import oracle" not in code, f
 
 
+def test_no_cxx_exception_crosses_the_boundary(pkg, tmp_path):
+    """Every status-returning entry point is a function-try-block (ptb_context.hpp: PTB_CATCH): a std::length_error /
+    std::bad_alloc inside the library comes back as a status, it does not unwind into a C / Go / ctypes caller."""
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    one = np.zeros(3, dtype=np.uint8)
+    out = tmp_path / "never.ppm"
+    # a 2^30 x 2^30 image as P3 text: 12 * 2^60 bytes, more than a std::vector can ever hold -- thrown before anything is read
+    rc = lib.ptb_write_ppm_rgb8(os.fsencode(str(out)), one.ctypes.data_as(ctypes.c_void_p), 1 << 30, 1 << 30, 0)
+    assert rc in (-6, -7)  # PTB_ERR_MEMORY / PTB_ERR_INTERNAL
+    assert not out.exists()  # and no file was opened for an image that could not be formatted
+
+
 def test_host_helpers_reject_bad_arguments(pkg):
     lib = ctypes.CDLL(pkg.LIB_PATH)
     assert lib.ptb_camera_with_config(None, None) == -1
