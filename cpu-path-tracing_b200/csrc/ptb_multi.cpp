@@ -212,12 +212,23 @@ int in_parallel(ptb_context* handle, F&& f)
     std::vector<int> rc(ms.size(), PTB_OK);
     std::vector<std::thread> th;
     th.reserve(ms.size());
-    for(size_t g = 1; g < ms.size(); ++g) {
-        th.emplace_back([&, g] { rc[g] = f(ms[g], static_cast<int>(g)); });
+    bool started = true;
+    try {
+        for(size_t g = 1; g < ms.size(); ++g) {
+            th.emplace_back([&, g] { rc[g] = f(ms[g], static_cast<int>(g)); }); // f is an entry point: it does not throw
+        }
     }
-    rc[0] = f(ms[0], 0);
+    catch(...) { // std::system_error: no thread to be had -- the ones that did start must still be joined
+        started = false;
+    }
+    if(started) {
+        rc[0] = f(ms[0], 0);
+    }
     for(std::thread& t : th) {
         t.join();
+    }
+    if(!started) {
+        return api_fail(handle, PTB_ERR_INTERNAL, "cannot start one host thread per GPU");
     }
     for(size_t g = 0; g < ms.size(); ++g) {
         if(rc[g] != PTB_OK) {
