@@ -27,8 +27,9 @@
 // by (seed, slot, sample) and travels with the path, so the image does not depend on any of this.
 //
 // Emission leaves the path state: it is added to the slot where it is picked up
-// (red.global.add.v4.f32 with weight 0) and the path's end adds the weight 1, so a parked
-// path is 14 words -- four float4 planes.
+// (red.global.add.v4.f32 with weight 0), and the sample COUNT of a slot is added once per tile when
+// the tile is fetched, so a path's end is silent unless it sees the sky -- a parked
+// path is 14 words, four planes.
 //
 // Ring accounting (all warp-uniform): tokens = lanes + READY + PARK.  Camera samples are only
 // generated when READY + PARK <= 32, so tokens <= 96.  At the top of the loop either every lane
@@ -268,9 +269,6 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                     }
                     // the ray scattered by the last iteration is never traced (main.cpp:111): the path ends here
                     out = dl1 < (static_cast<uint32_t>(kDepthLimit) << 24);
-                    if(!out) {
-                        red_add_v4(prm.accum + __float_as_uint(eb.w), 0.0f, 0.0f, 0.0f, 1.0f);
-                    }
                 }
                 uint32_t const om = __ballot_sync(kFull, out);
                 if(out) {
@@ -305,6 +303,10 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                         gen_valid = min(32u, prm.nslots - group * 32u); // the slots of a tile are a prefix of its lanes
                         if(lane < gen_valid) {
                             slot_coords(gen_slot, prm.width, prm.ns, gen_x, gen_y, gen_sx, gen_sy);
+                            // the slot's sample count (main.cpp:192 divides by it) is credited HERE, once per tile, for all the
+                            // samples this lane will start: a path that ends by roulette or at the depth limit then ends
+                            // silently -- no divergent "weight 1" add at 3 of 32 lanes in nine of ten iterations
+                            red_add_v4(prm.accum + gen_slot, 0.0f, 0.0f, 0.0f, static_cast<float>(tile_samples));
                         }
                     }
                 }
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 // main.cpp:116-119 sky gradient on the unit direction; the path ends
                 float const tt = 0.5f * (p.dy + 1.0f);
                 float const omt = 1.0f - tt;
-                red_add_v4(prm.accum + slot, p.tr * fmaf(0.5f, tt, omt), p.tg * fmaf(0.7f, tt, omt), p.tb * (omt + tt), 1.0f);
+                red_add_v4(prm.accum + slot, p.tr * fmaf(0.5f, tt, omt), p.tg * fmaf(0.7f, tt, omt), p.tb * (omt + tt), 0.0f);
                 ended = true;
             }
             else {
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kSortedThreads, kSortedBlocksPerSm) mega_sorte
                 p.tg *= col.y;
                 p.tb *= col.z;
                 if(ended) {
-                    red_add_v4(prm.accum + slot, 0.0f, 0.0f, 0.0f, 1.0f);
+                    // main.cpp:131-133: the path dies; its sample was counted when its tile was fetched
                 }
                 else if(((tag ^ kInline) & 0xff) == 0 && dl < (static_cast<uint32_t>(kDepthLimit - 1) << 24)) {
                     float4 const sa = shade(0, id);
