@@ -880,6 +880,43 @@ def test_two_contexts_on_one_gpu_from_two_threads(gpu):
         assert np.isclose(acc_t[:, :3], acc_a[:, :3], rtol=1e-5, atol=1e-5).all()
 
 
+def test_camera_inside_a_mirror_ball_keeps_full_precision_keys(gpu):
+    """dev/fuzz_scenes.py seed 51 scene 1: a r = 0.0016 lamp and a camera inside a r = 0.25 mirror ball whose colour exceeds 1
+    (no roulette death: 99 reflections per path off one concave surface).  With the list position riding in the key's low
+    mantissa bits every hit distance is truncated the same way and the chord pattern drifts: the run-time compiled kernel
+    lit 23 % of the pixels, the FP64 oracle and the full-precision keys 1 %.  Such scenes must not take the index-in-key
+    layout, and the run-time build must trace what the precompiled kernels trace."""
+    sph = np.zeros(3, dtype=gpu.SPHERE_DTYPE)
+    sph["radius"] = [0.25, 0.014588611048801227, 0.001619232652198674]
+    sph["position"] = [[-0.03296013, -0.07278335, -0.03793183], [-0.06246247, 0.00336563, -0.02177486],
+                       [-0.06036928, 0.02285544, -0.0830866]]
+    sph["color"] = [[1.04220626, 1.04026928, 1.18389618], [0.93259856, 0.83243481, 0.71187968], [0.23217308, 0.28617143, 0.50365051]]
+    sph["emission"][2] = 1e6
+    sph["reflection"] = 1
+    W, H, S = 11, 67, 9
+    _, cfg = gpu.builtin_scene("simple", W, H)
+    cfg["position"][0] = [-0.05835709, 0.0216139, -0.08301402]
+    cfg["direction"][0] = [-0.05715281, 0.02583565, -0.08152568]
+    cfg["aperture"][0] = 0.0
+    cfg["vertical_fov_radians"][0] = 0.97654284
+    cfg["focus_distance"][0] = 0.19112383
+    cam = gpu.camera_with_config(cfg)
+    lit = {}
+    with make_renderer(gpu, sph, cam, W, H) as r:
+        assert r.scene_layout()["embed_ok"] == 0
+        for label, flags, reps in (("precompiled", gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED | gpu.CODEGEN_PRECOMPILED, 1),
+                                   ("run-time", gpu.PRECISION_FP32 | gpu.VARIANT_MEGAKERNEL_SORTED, 2),
+                                   ("fp64", gpu.PRECISION_FP64, 1)):
+            for _ in range(reps):
+                r.clear()
+                r.render(8, 0, S, flags)
+            lit[label] = (r.stats().rays, float((r.resolve() > 0.5).mean()))
+        assert r.jit_info()["compiled"] >= 1
+    assert lit["run-time"][0] == lit["precompiled"][0]          # the same rays, to the last one
+    assert lit["run-time"][1] == lit["precompiled"][1]
+    assert abs(lit["precompiled"][1] - lit["fp64"][1]) < 0.02   # a per cent of the pixels see the lamp, not a quarter
+
+
 def test_error_behaviour(gpu):
     with gpu.Renderer(0) as r:
         with pytest.raises(gpu.PtbError) as e:
