@@ -60,6 +60,20 @@ def test_product_never_imports_the_oracle():
                 assert "pt_oracle" not in code and "libptref" not in code and "import oracle" not in code, f
 
 
+def test_binding_constants_are_the_header_s(pkg):
+    """Every PTB_X = value of include/ptb200.h that the ctypes binding mirrors (flags, transports, sizes) has that value there."""
+    import re
+    text = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    header = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"\bPTB_([A-Z0-9_]+)\s*=\s*(-?(?:0x[0-9A-Fa-f]+|\d+))", text)}
+    header.update({m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+PTB_([A-Z0-9_]+)\s+(\d+)\b", text)})
+    mirrored = [n for n in header if hasattr(pkg, n) and isinstance(getattr(pkg, n), int)]
+    assert {"VARIANT_MEGAKERNEL_SORTED", "PRECISION_FP64", "INTEGRATOR_SMALLPT", "ACCEL_SCAN", "CODEGEN_PRECOMPILED", "TRANSPORT_PEER",
+            "SPHERE_BYTES", "CAMERA_BYTES", "COMM_ID_BYTES"} <= set(mirrored)
+    for n in mirrored:
+        assert getattr(pkg, n) == header[n], n
+    assert header["ERR_MEMORY"] == -6 and header["ERR_INTERNAL"] == -7 and header["OK"] == 0
+
+
 def test_no_cxx_exception_crosses_the_boundary(pkg, tmp_path):
     """Every status-returning entry point is a function-try-block (ptb_context.hpp: PTB_CATCH): a std::length_error /
     std::bad_alloc inside the library comes back as a status, it does not unwind into a C / Go / ctypes caller."""
