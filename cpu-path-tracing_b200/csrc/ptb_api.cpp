@@ -957,9 +957,10 @@ try {
         }
     }
     ctx->buffers_epoch++;
-    ctx->width = width;
-    ctx->height = height;
-    ctx->ns = num_subpixels;
+    // from here until every buffer of the new geometry exists there is NO image: an allocation that fails half way
+    // (out of memory at 8K) must not leave the new size over missing buffers -- require_ready() then says "no image"
+    ctx->width = 0;
+    ctx->height = 0;
     ctx->nslots = static_cast<size_t>(width) * static_cast<size_t>(height) * static_cast<size_t>(num_subpixels * num_subpixels);
     size_t const bytes = ctx->nslots * sizeof(float4);
     if(bytes > ctx->d_accum_bytes) {
@@ -983,6 +984,9 @@ try {
         ctx->ext_accum = nullptr;
         ctx->ext_accum_bytes = 0;
     }
+    ctx->width = width;
+    ctx->height = height;
+    ctx->ns = num_subpixels;
     if(ctx->have_scene && ctx->have_sbcam) {
         int const rc = rebuild_or_invalidate(ctx); // near-root-only classification depends on the aspect ratio
         if(rc != PTB_OK) {
